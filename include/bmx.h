@@ -1,0 +1,183 @@
+/*
+ * bmx.h -- C ABI of libbmx.so, the B200-native (sm_100a) replacement for the one data-parallel
+ * hot path of AnupBS28/PARALLEL_IMPLEMENTATION_OF_STRING_MATCHING_ALGORITHMS_OPENCL: the
+ * partitioned Boyer-Moore text scan of BoyreMoore/.
+ *
+ * The reference has no plugin/FFI layer.  Its boundary is the OpenCL kernel entry
+ *     search(text, pattern, se, ans, gstable, bstable, sublength)      x64/Debug/kernel1.cl:1
+ * driven by the host glue in BoyreMoore/BoyreMoore/BoyreMoore.cpp:192-313 (buffers :233-252,
+ * arguments :264-270, launch :273-280, read-back :286).  Every entry point below names the
+ * reference lines it replaces.  "BoyreMoore.cpp" means BoyreMoore/BoyreMoore/BoyreMoore.cpp and
+ * "kernel1.cl" means BoyreMoore/x64/Debug/kernel1.cl (the copy the shipped exe loads).
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types (a stream travels as void* = cudaStream_t).
+ *   - return 0 (BMX_OK) or a negative bmx_status; never throws; bmx_last_error() (thread-local)
+ *     explains the last failure on the calling thread.
+ *   - positions are 0-based byte offsets of the match START, ascending, overlapping occurrences
+ *     all reported (kernel1.cl:24 advances by exactly one after a match).
+ *   - the caller owns every buffer it passes; the library owns only handles it created.
+ *   - there is NO CPU fallback: without a CUDA device every scanning call fails with
+ *     BMX_E_NODEVICE / BMX_E_CUDA.
+ */
+#ifndef BMX_H
+#define BMX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMX_VERSION 100 /* 0.1.0 */
+
+typedef enum bmx_status {
+    BMX_OK = 0,
+    BMX_E_BADARG = -1,    /* NULL where data is required, m <= 0, n < 0, m > BMX_MAX_PATTERN ... */
+    BMX_E_CUDA = -2,      /* a CUDA runtime call failed; see bmx_last_error() */
+    BMX_E_NOMEM = -3,     /* host or device allocation failed */
+    BMX_E_NODEVICE = -4,  /* no CUDA device visible */
+    BMX_E_TABLES = -5     /* caller-supplied gs/bs tables differ from the ones this pattern needs */
+} bmx_status;
+
+/* Longest supported pattern (the reference stops at 99: char word[100], BoyreMoore.cpp:144). */
+#define BMX_MAX_PATTERN (1 << 20)
+
+/* Scan variants.  AUTO picks by pattern length from measured throughput. */
+typedef enum bmx_variant {
+    BMX_VARIANT_AUTO = 0,
+    BMX_VARIANT_QGRAM = 1,    /* m >= 7: aligned q-gram hash filter + warp ballot + BM-skip verify */
+    BMX_VARIANT_WINDOW = 2,   /* any m : per-position <=4-byte window filter (+ BM-skip verify) */
+    BMX_VARIANT_SHIFTAND = 3  /* m <= 32: bit-parallel Shift-And (the Shift-Or family) */
+} bmx_variant;
+
+/* Per-call measurements filled by the *_ex / scanner calls (all optional). */
+typedef struct bmx_stats {
+    float device_ms;       /* CUDA-event time of memset + scan kernel(s) on the launching stream */
+    int32_t variant;       /* bmx_variant actually run */
+    int32_t kernel_launches; /* scan kernels launched by the call */
+    int32_t grid;          /* CTAs of the (last) scan kernel */
+    int32_t stages;        /* TMA pipeline stages per CTA */
+    int32_t tile_bytes;    /* text bytes per tile */
+    int32_t smem_bytes;    /* dynamic shared memory per CTA */
+    int64_t tiles;         /* tiles scanned */
+} bmx_stats;
+
+int bmx_version(void);
+const char *bmx_last_error(void);
+
+/* Number of visible CUDA devices (0 when there is none; never fails). */
+int bmx_device_count(void);
+
+/*
+ * Pattern pre-processing, once per pattern -- replaces BoyreMoore.cpp:153-162 (bad-symbol
+ * table) and :165-190 with helpers :16-60 (good-suffix table).
+ *   bad[c]  = m for every byte value c, then bad[P[i]] = m-1-i for i = 0..m-2  (256 entries,
+ *             indexed by unsigned byte; the reference has 128 entries indexed by signed char).
+ *   good[k] = the reference's strong good-suffix shift after k matched suffix bytes,
+ *             k = 1..m-1; good[0] = 0 (the reference leaves it uninitialised and unused).
+ * Pure host code, O(m) time; values identical to the reference's O(m^3) construction.
+ */
+int bmx_build_tables(const char *pat, int32_t m, int32_t bad[256], int32_t *good /* m ints */);
+
+/*
+ * Host-pointer search -- replaces the whole of BoyreMoore.cpp:192-313: device buffers,
+ * host->device copies, launch, read-back.  text/pat/pos_out/count_out are HOST pointers.
+ * Finds every start p in [0, n-m] with text[p..p+m) == pat, i.e. the reference's serial result
+ * (one partition {0, n-1}).  *count_out is always the full count; at most pos_cap positions are
+ * written (the smallest ones); pos_out may be NULL for count-only.  m > n is not an error
+ * (count 0, kernel1.cl:15,19); m <= 0 is BMX_E_BADARG.  Synchronous.  The host->device copy is
+ * chunked and overlapped with scanning (pinned memory is used directly, pageable memory goes
+ * through pinned bounce buffers).
+ */
+int bmx_search(const char *text, int64_t n, const char *pat, int32_t m,
+               int64_t *pos_out, int64_t pos_cap, uint64_t *count_out);
+
+/* As bmx_search, on an explicit device, with variant choice and measurements. */
+int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int32_t m,
+                  int64_t *pos_out, int64_t pos_cap, uint64_t *count_out,
+                  int32_t variant, bmx_stats *stats);
+
+/*
+ * Device-resident search -- replaces BoyreMoore.cpp:258-286 (kernel creation, clSetKernelArg,
+ * clEnqueueNDRangeKernel, blocking read of the counts) for text already in device memory.
+ * d_text and d_pos_out are DEVICE pointers on the current device (any alignment); pat and
+ * count_out are host pointers.  Launches on `stream` (cudaStream_t, NULL = default stream),
+ * then waits for it to read the count back.  *device_ms (optional) receives the CUDA-event
+ * time of the scan.  d_pos_out may be NULL (count-only, no output traffic).
+ */
+int bmx_search_device(const void *d_text, int64_t n, const char *pat, int32_t m,
+                      int64_t *d_pos_out, int64_t pos_cap, uint64_t *count_out,
+                      float *device_ms, void *stream);
+
+/* As bmx_search_device with: pos_base added to every reported position (multi-GPU shards report
+ * global offsets), explicit variant, full measurements. */
+int bmx_search_device_ex(const void *d_text, int64_t n, const char *pat, int32_t m,
+                         int64_t pos_base, int64_t *d_pos_out, int64_t pos_cap,
+                         uint64_t *count_out, int32_t variant, bmx_stats *stats, void *stream);
+
+/*
+ * Argument-for-argument mirror of the kernel entry (kernel1.cl:1; host argument order
+ * BoyreMoore.cpp:264-270): text, pattern, se, ans, gstable, bstable, sublength -- plus the
+ * work-item count the reference passes as global_item_size (BoyreMoore.cpp:273).
+ *   se[2*id], se[2*id+1] = INCLUSIVE byte range of work-item id (BoyreMoore.cpp:119-141);
+ *   ans[id] = number of occurrences lying fully inside that range (no halo: this is the
+ *   reference's partitioned behaviour, seam losses included).
+ * All pointers are HOST pointers.  text must hold at least max(se[2*id+1])+1 bytes.
+ * gs (m ints, entries 1..m-1 checked) and bs (128 ints, the reference's size) may be NULL; when
+ * given they must equal the tables this pattern needs, else BMX_E_TABLES (the device scan uses
+ * its own copy, so a wrong table cannot silently change the result).
+ */
+int bmx_search_partitions(const char *text, const char *pat, const int32_t *se, int32_t *ans,
+                          const int32_t *gs, const int32_t *bs, int32_t m, int32_t nparts);
+
+/*
+ * The reference's host-side word partitioner -- replaces BoyreMoore.cpp:94-141.  Splits
+ * text[0..n) (up to the first NUL, like the reference's strcpy'd copy, :89-90) on single spaces
+ * into nparts inclusive byte ranges of equal word count: se[2*p], se[2*p+1].  The space between
+ * two ranges belongs to neither; left-over words are dropped.  Pure host code.  Only needed to
+ * feed bmx_search_partitions the numbers the reference would have used; the scan itself tiles
+ * the text with an (m-1)-byte halo instead.
+ */
+int bmx_partition_words(const char *text, int64_t n, int32_t nparts, int32_t *se /* 2*nparts */);
+
+/*
+ * Reusable scanner: keeps the per-pattern device block (pattern, tables, filter constants), the
+ * look-back scratch and the events across calls, and exposes the asynchronous pieces so a caller
+ * can chain chunk scans on its own stream (this is what bmx_search builds on).
+ * One scanner per host thread / stream; scanners are independent of each other.
+ */
+typedef struct bmx_scanner bmx_scanner;
+
+int bmx_scanner_create(int device, bmx_scanner **out);
+void bmx_scanner_destroy(bmx_scanner *s);
+
+/* Builds the tables (bmx_build_tables) and uploads the pattern block on `stream`. */
+int bmx_scanner_set_pattern(bmx_scanner *s, const char *pat, int32_t m, int32_t variant, void *stream);
+
+/* Starts a new result: zeroes the running count.  Positions of later bmx_scanner_scan calls are
+ * appended to d_pos_out in call order (so scanning consecutive chunks left to right keeps the
+ * list ascending). */
+int bmx_scanner_begin(bmx_scanner *s, int64_t *d_pos_out, int64_t pos_cap, void *stream);
+
+/* Asynchronously scans d_text[0..n) for matches STARTING in [0, n-m]; reports start + pos_base.
+ * No host synchronisation. */
+int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_base, void *stream);
+
+/* Waits for `stream`, returns the running count and (optional) statistics of the scans since
+ * bmx_scanner_begin. */
+int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, void *stream);
+
+/*
+ * Synthetic text generator used by the tests and bench.py (identical definition on the CPU in
+ * oracle/bm_oracle.c:oracle_synth_fill): fills d_text[0..len) with the bytes at absolute
+ * offsets [offset, offset+len) of the stream defined by (seed, alphabet[sigma]).
+ * Not part of the reference; it exists so that 4 GiB .. 64 GiB inputs never cross PCIe.
+ */
+int bmx_synth_fill_device(void *d_text, int64_t offset, int64_t len, uint64_t seed,
+                          const unsigned char *alphabet, int32_t sigma, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMX_H */

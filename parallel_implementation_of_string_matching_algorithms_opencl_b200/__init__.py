@@ -1,0 +1,12 @@
+"""B200-native exact pattern matching: the Boyer-Moore scan path of
+AnupBS28/PARALLEL_IMPLEMENTATION_OF_STRING_MATCHING_ALGORITHMS_OPENCL rebuilt as hand-written
+sm_100a CUDA behind a C ABI (include/bmx.h).  See DESIGN.md and INTEGRATION.md."""
+from . import _lib, synth  # noqa: F401
+from ._lib import BmxError, LIB_PATH  # noqa: F401
+from .host import (Scanner, build_tables, device_count, partition_words, search,  # noqa: F401
+                   search_device, search_partitions, version)
+
+__all__ = [
+    "BmxError", "LIB_PATH", "Scanner", "build_tables", "device_count", "partition_words",
+    "search", "search_device", "search_partitions", "version", "synth",
+]

@@ -1,0 +1,598 @@
+// bmx_abi.cu -- the C ABI of libbmx.so (include/bmx.h): host glue over the scan kernels.
+//
+// Replaces the reference's OpenCL host layer, BoyreMoore/BoyreMoore/BoyreMoore.cpp:192-313
+// (context/queue :213-231, buffers :233-244, blocking writes :246-252, kernel + arguments
+// :261-270, NDRange launch :273-280, blocking read of the counts :286, releases :299-312).
+// There is no CPU fallback anywhere in this file: every scanning entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "bmx_internal.h"
+
+namespace bmx {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char tl_error[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(tl_error, sizeof tl_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define BMX_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? BMX_E_NOMEM : BMX_E_CUDA, "%s: %s", #call,     \
+                        cudaGetErrorString(e_));                                                         \
+    } while (0)
+
+static int check_device(int device)
+{
+    int n = 0;
+    const cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        (void)cudaGetLastError();
+        return fail(BMX_E_NODEVICE, "no CUDA device visible (%s); libbmx has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(BMX_E_BADARG, "device %d out of range (0..%d)", device, n - 1);
+    return BMX_OK;
+}
+
+}  // namespace bmx
+
+using namespace bmx;
+
+// ---------------------------------------------------------------------------------------------
+// scanner
+// ---------------------------------------------------------------------------------------------
+struct bmx_scanner {
+    int device = 0;
+    // per-pattern state
+    int32_t m = 0;
+    int variant = 0;
+    std::vector<unsigned char> pat;
+    void *d_block = nullptr;  // [bad 256 x i32][good m x i32][pattern m bytes]
+    size_t d_block_cap = 0;
+    ScanArgs proto{};         // filter constants + pattern pointers
+    // result state
+    unsigned long long *d_ctrl = nullptr;  // [0],[1] carry ping-pong, [2] count-only accumulator
+    unsigned long long *h_result = nullptr;  // pinned
+    void *d_scratch = nullptr;  // [ticket counter 8 B][tile_state ...]
+    size_t d_scratch_cap = 0;
+    int64_t *d_pos_out = nullptr;
+    int64_t pos_cap = 0;
+    bool positions = false;
+    uint32_t scan_index = 0;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    bool timing_open = false;
+    bmx_stats stats{};
+};
+
+extern "C" {
+
+int bmx_version(void) { return BMX_VERSION; }
+
+const char *bmx_last_error(void) { return tl_error; }
+
+int bmx_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int bmx_build_tables(const char *pat, int32_t m, int32_t bad[256], int32_t *good)
+{
+    if (!pat || m <= 0 || m > BMX_MAX_PATTERN || !bad || !good)
+        return fail(BMX_E_BADARG, "bmx_build_tables: pat/bad/good must be non-NULL and 1 <= m <= %d", BMX_MAX_PATTERN);
+    build_bad_table(reinterpret_cast<const unsigned char *>(pat), m, bad);
+    build_good_table(reinterpret_cast<const unsigned char *>(pat), m, good);
+    return BMX_OK;
+}
+
+int bmx_scanner_create(int device, bmx_scanner **out)
+{
+    if (!out) return fail(BMX_E_BADARG, "bmx_scanner_create: out is NULL");
+    *out = nullptr;
+    if (int rc = check_device(device)) return rc;
+    BMX_CUDA(cudaSetDevice(device));
+    bmx_scanner *s = new (std::nothrow) bmx_scanner();
+    if (!s) return fail(BMX_E_NOMEM, "out of host memory");
+    s->device = device;
+    cudaError_t e = cudaMalloc(&s->d_ctrl, 64);
+    if (e == cudaSuccess) e = cudaHostAlloc(&s->h_result, 64, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_stop);
+    if (e != cudaSuccess) {
+        bmx_scanner_destroy(s);
+        return fail(e == cudaErrorMemoryAllocation ? BMX_E_NOMEM : BMX_E_CUDA, "bmx_scanner_create: %s",
+                    cudaGetErrorString(e));
+    }
+    *out = s;
+    return BMX_OK;
+}
+
+void bmx_scanner_destroy(bmx_scanner *s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->d_block) cudaFree(s->d_block);
+    if (s->d_scratch) cudaFree(s->d_scratch);
+    if (s->d_ctrl) cudaFree(s->d_ctrl);
+    if (s->h_result) cudaFreeHost(s->h_result);
+    if (s->ev_start) cudaEventDestroy(s->ev_start);
+    if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    delete s;
+}
+
+int bmx_scanner_set_pattern(bmx_scanner *s, const char *pat, int32_t m, int32_t variant, void *stream)
+{
+    if (!s || !pat) return fail(BMX_E_BADARG, "bmx_scanner_set_pattern: NULL argument");
+    if (m <= 0 || m > BMX_MAX_PATTERN)
+        return fail(BMX_E_BADARG, "pattern length %d outside 1..%d (an empty pattern is rejected)", m, BMX_MAX_PATTERN);
+    if (variant < BMX_VARIANT_AUTO || variant > BMX_VARIANT_SHIFTAND)
+        return fail(BMX_E_BADARG, "unknown variant %d", variant);
+    BMX_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    const unsigned char *p = reinterpret_cast<const unsigned char *>(pat);
+    s->m = m;
+    s->variant = resolve_variant(variant, m);
+    s->pat.assign(p, p + m);
+
+    // Host image of the device block: tables once per pattern (BoyreMoore.cpp:153-190).
+    const size_t good_off = 256 * sizeof(int32_t);
+    const size_t pat_off = good_off + (size_t)m * sizeof(int32_t);
+    const size_t bytes = (pat_off + (size_t)m + 15) & ~size_t(15);
+    std::vector<unsigned char> image(bytes, 0);
+    build_bad_table(p, m, reinterpret_cast<int32_t *>(image.data()));
+    build_good_table(p, m, reinterpret_cast<int32_t *>(image.data() + good_off));
+    memcpy(image.data() + pat_off, p, (size_t)m);
+
+    if (bytes > s->d_block_cap) {
+        // the old block may still be read by scans in flight on `stream`
+        BMX_CUDA(cudaStreamSynchronize(st));
+        if (s->d_block) cudaFree(s->d_block);
+        s->d_block = nullptr;
+        s->d_block_cap = 0;
+        BMX_CUDA(cudaMalloc(&s->d_block, bytes));
+        s->d_block_cap = bytes;
+    }
+    // pageable source: the runtime stages it before returning, so `image` may die afterwards
+    BMX_CUDA(cudaMemcpyAsync(s->d_block, image.data(), bytes, cudaMemcpyHostToDevice, st));
+
+    s->proto = ScanArgs{};
+    s->proto.m = m;
+    s->proto.g_bad = reinterpret_cast<const int32_t *>(s->d_block);
+    s->proto.g_good = reinterpret_cast<const int32_t *>(static_cast<unsigned char *>(s->d_block) + good_off);
+    s->proto.g_pat = static_cast<const uint8_t *>(s->d_block) + pat_off;
+    fill_filter_constants(s->variant, p, m, &s->proto);
+    return BMX_OK;
+}
+
+int bmx_scanner_begin(bmx_scanner *s, int64_t *d_pos_out, int64_t pos_cap, void *stream)
+{
+    if (!s) return fail(BMX_E_BADARG, "bmx_scanner_begin: NULL scanner");
+    if (pos_cap < 0) return fail(BMX_E_BADARG, "pos_cap < 0");
+    BMX_CUDA(cudaSetDevice(s->device));
+    s->d_pos_out = d_pos_out;
+    s->pos_cap = d_pos_out ? pos_cap : 0;
+    s->positions = d_pos_out != nullptr;
+    s->scan_index = 0;
+    s->timing_open = false;
+    s->stats = bmx_stats{};
+    s->stats.variant = s->variant;
+    BMX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, 64, static_cast<cudaStream_t>(stream)));
+    return BMX_OK;
+}
+
+int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_base, void *stream)
+{
+    if (!s || s->m <= 0) return fail(BMX_E_BADARG, "bmx_scanner_scan: scanner has no pattern");
+    if (n < 0 || (!d_text && n > 0)) return fail(BMX_E_BADARG, "bmx_scanner_scan: bad text (n=%lld)", (long long)n);
+    if (n < s->m) return BMX_OK;  // kernel1.cl:15,19: the loop is never entered
+    BMX_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+    ScanArgs a = s->proto;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(d_text);
+    const int64_t lead = (int64_t)(addr & 15u);
+    a.vtext = reinterpret_cast<const uint8_t *>(addr - (uintptr_t)lead);
+    a.vlen = lead + n;
+    a.vmin = lead;
+    a.vmax = lead + n - s->m;
+    a.pos_bias = pos_base - lead;
+    a.pos_out = s->d_pos_out;
+    a.pos_cap = s->pos_cap;
+
+    ScanLaunch launch{};
+    if (int rc = plan_scan(s->device, s->variant, s->m, s->positions, &a, &launch)) return rc;
+
+    const size_t scratch = 8 + (s->positions ? (size_t)a.num_tiles * 8 : 0);
+    if (scratch > s->d_scratch_cap) {
+        BMX_CUDA(cudaStreamSynchronize(st));
+        if (s->d_scratch) cudaFree(s->d_scratch);
+        s->d_scratch = nullptr;
+        s->d_scratch_cap = 0;
+        const size_t want = std::max<size_t>(scratch + scratch / 4, 1 << 20);
+        BMX_CUDA(cudaMalloc(&s->d_scratch, want));
+        s->d_scratch_cap = want;
+    }
+    a.tile_counter = static_cast<uint32_t *>(s->d_scratch);
+    a.tile_state = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(s->d_scratch) + 8);
+    a.carry_in = s->d_ctrl + (s->scan_index & 1u);
+    a.carry_out = s->d_ctrl + ((s->scan_index + 1u) & 1u);
+    a.count_acc = s->d_ctrl + 2;
+
+    if (!s->timing_open) {
+        BMX_CUDA(cudaEventRecord(s->ev_start, st));
+        s->timing_open = true;
+    }
+    BMX_CUDA(cudaMemsetAsync(s->d_scratch, 0, scratch, st));
+    if (int rc = launch_scan(a, launch, s->positions, st)) return rc;
+    BMX_CUDA(cudaEventRecord(s->ev_stop, st));
+
+    s->scan_index += 1;
+    s->stats.kernel_launches += 1;
+    s->stats.grid = launch.grid;
+    s->stats.stages = (int32_t)a.stages;
+    s->stats.tile_bytes = launch.tile_bytes;
+    s->stats.smem_bytes = (int32_t)launch.smem_bytes;
+    s->stats.tiles += a.num_tiles;
+    return BMX_OK;
+}
+
+int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, void *stream)
+{
+    if (!s || !count_out) return fail(BMX_E_BADARG, "bmx_scanner_finish: NULL argument");
+    BMX_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned long long *src = s->positions ? s->d_ctrl + (s->scan_index & 1u) : s->d_ctrl + 2;
+    BMX_CUDA(cudaMemcpyAsync(s->h_result, src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    BMX_CUDA(cudaStreamSynchronize(st));
+    *count_out = (uint64_t)s->h_result[0];
+    if (s->timing_open) {
+        float ms = 0.f;
+        BMX_CUDA(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
+        s->stats.device_ms = ms;
+    }
+    if (stats) *stats = s->stats;
+    return BMX_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// one cached scanner + streams per (host thread, device) for the convenience entry points
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kMaxDevices = 64;
+constexpr int kBounce = 3;
+
+struct ThreadCtx {
+    bmx_scanner *scanner = nullptr;
+    cudaStream_t copy_stream = nullptr, scan_stream = nullptr;
+    std::vector<cudaEvent_t> events;
+    unsigned char *bounce[kBounce] = {nullptr, nullptr, nullptr};
+    size_t bounce_bytes = 0;
+    bool pool_tuned = false;
+};
+thread_local ThreadCtx tl_ctx[kMaxDevices];
+
+int get_ctx(int device, ThreadCtx **out)
+{
+    if (int rc = check_device(device)) return rc;
+    if (device >= kMaxDevices) return fail(BMX_E_BADARG, "device index %d too large", device);
+    ThreadCtx &c = tl_ctx[device];
+    BMX_CUDA(cudaSetDevice(device));
+    if (!c.scanner) {
+        if (int rc = bmx_scanner_create(device, &c.scanner)) return rc;
+    }
+    *out = &c;
+    return BMX_OK;
+}
+
+int ensure_streams(ThreadCtx &c, int device, size_t nevents)
+{
+    if (!c.copy_stream) BMX_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+    if (!c.scan_stream) BMX_CUDA(cudaStreamCreateWithFlags(&c.scan_stream, cudaStreamNonBlocking));
+    while (c.events.size() < nevents) {
+        cudaEvent_t e;
+        BMX_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        c.events.push_back(e);
+    }
+    if (!c.pool_tuned) {
+        // keep freed blocks in the stream-ordered pool: the multi-GiB text buffer is reused
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+        c.pool_tuned = true;
+    }
+    return BMX_OK;
+}
+
+bool is_pinned_host(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bmx_search_device_ex(const void *d_text, int64_t n, const char *pat, int32_t m, int64_t pos_base,
+                         int64_t *d_pos_out, int64_t pos_cap, uint64_t *count_out, int32_t variant,
+                         bmx_stats *stats, void *stream)
+{
+    if (!count_out || !pat) return fail(BMX_E_BADARG, "bmx_search_device: pat/count_out must be non-NULL");
+    if (n < 0 || (!d_text && n > 0)) return fail(BMX_E_BADARG, "bmx_search_device: bad text (n=%lld)", (long long)n);
+    if (pos_cap < 0) return fail(BMX_E_BADARG, "pos_cap < 0");
+    int device = 0;
+    if (int rc = check_device(0)) return rc;
+    BMX_CUDA(cudaGetDevice(&device));
+    ThreadCtx *c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    if (int rc = bmx_scanner_set_pattern(c->scanner, pat, m, variant, stream)) return rc;
+    if (int rc = bmx_scanner_begin(c->scanner, d_pos_out, pos_cap, stream)) return rc;
+    if (int rc = bmx_scanner_scan(c->scanner, d_text, n, pos_base, stream)) return rc;
+    return bmx_scanner_finish(c->scanner, count_out, stats, stream);
+}
+
+int bmx_search_device(const void *d_text, int64_t n, const char *pat, int32_t m, int64_t *d_pos_out,
+                      int64_t pos_cap, uint64_t *count_out, float *device_ms, void *stream)
+{
+    bmx_stats st{};
+    const int rc = bmx_search_device_ex(d_text, n, pat, m, 0, d_pos_out, pos_cap, count_out, BMX_VARIANT_AUTO, &st, stream);
+    if (rc == BMX_OK && device_ms) *device_ms = st.device_ms;
+    return rc;
+}
+
+int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int32_t m, int64_t *pos_out,
+                  int64_t pos_cap, uint64_t *count_out, int32_t variant, bmx_stats *stats)
+{
+    if (!count_out || !pat) return fail(BMX_E_BADARG, "bmx_search: pat/count_out must be non-NULL");
+    if (n < 0 || (!text && n > 0)) return fail(BMX_E_BADARG, "bmx_search: bad text (n=%lld)", (long long)n);
+    if (pos_cap < 0) return fail(BMX_E_BADARG, "pos_cap < 0");
+    if (m <= 0 || m > BMX_MAX_PATTERN)
+        return fail(BMX_E_BADARG, "pattern length %d outside 1..%d (an empty pattern is rejected)", m, BMX_MAX_PATTERN);
+    ThreadCtx *c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    *count_out = 0;
+    if (stats) *stats = bmx_stats{};
+    if (n < m) return BMX_OK;
+
+    int64_t chunk = (int64_t)64 << 20;
+    if (const char *e = getenv("BMX_H2D_CHUNK_MB")) {
+        const long mb = atol(e);
+        if (mb > 0) chunk = (int64_t)mb << 20;
+    }
+    chunk = std::max<int64_t>(chunk, (int64_t)m * 2);
+    const int64_t nchunks = (n + chunk - 1) / chunk;
+    if (int rc = ensure_streams(*c, device, (size_t)nchunks + kBounce + 1)) return rc;
+
+    const int64_t max_hits = n - m + 1;
+    const int64_t dev_cap = pos_out ? std::min(pos_cap, max_hits) : 0;
+    unsigned char *d_text = nullptr;
+    int64_t *d_pos = nullptr;
+    int rc = BMX_OK;
+    auto cleanup = [&]() {
+        if (d_text) cudaFreeAsync(d_text, c->scan_stream);
+        if (d_pos) cudaFreeAsync(d_pos, c->scan_stream);
+        cudaStreamSynchronize(c->scan_stream);
+    };
+#define BMX_TRY(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            rc = fail(e_ == cudaErrorMemoryAllocation ? BMX_E_NOMEM : BMX_E_CUDA, "%s: %s", #call, \
+                      cudaGetErrorString(e_));                                               \
+            cleanup();                                                                       \
+            return rc;                                                                       \
+        }                                                                                    \
+    } while (0)
+
+    BMX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_text), (size_t)n + 16, c->scan_stream));
+    if (dev_cap > 0) BMX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_pos), (size_t)dev_cap * 8, c->scan_stream));
+    // the copy stream must not touch d_text before the allocation is ordered
+    BMX_TRY(cudaEventRecord(c->events[(size_t)nchunks + kBounce], c->scan_stream));
+    BMX_TRY(cudaStreamWaitEvent(c->copy_stream, c->events[(size_t)nchunks + kBounce], 0));
+
+    if ((rc = bmx_scanner_set_pattern(c->scanner, pat, m, variant, c->scan_stream)) != BMX_OK ||
+        (rc = bmx_scanner_begin(c->scanner, dev_cap > 0 ? d_pos : nullptr, dev_cap, c->scan_stream)) != BMX_OK) {
+        cleanup();
+        return rc;
+    }
+
+    const bool pinned = is_pinned_host(text);
+    if (!pinned && c->bounce_bytes < (size_t)std::min(chunk, n)) {
+        for (int b = 0; b < kBounce; ++b) {
+            if (c->bounce[b]) cudaFreeHost(c->bounce[b]);
+            c->bounce[b] = nullptr;
+        }
+        c->bounce_bytes = 0;
+        for (int b = 0; b < kBounce; ++b) BMX_TRY(cudaHostAlloc(reinterpret_cast<void **>(&c->bounce[b]), (size_t)std::min(chunk, n), cudaHostAllocDefault));
+        c->bounce_bytes = (size_t)std::min(chunk, n);
+    }
+
+    int64_t scanned = 0;  // start positions < scanned are done
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int64_t off = k * chunk;
+        const int64_t len = std::min(chunk, n - off);
+        const char *src = text + off;
+        if (!pinned) {
+            const int b = (int)(k % kBounce);
+            // the bounce buffer is free once the copy that used it kBounce chunks ago has finished
+            if (k >= kBounce) BMX_TRY(cudaEventSynchronize(c->events[(size_t)nchunks + (size_t)b]));
+            memcpy(c->bounce[b], src, (size_t)len);
+            src = reinterpret_cast<const char *>(c->bounce[b]);
+            BMX_TRY(cudaMemcpyAsync(d_text + off, src, (size_t)len, cudaMemcpyHostToDevice, c->copy_stream));
+            BMX_TRY(cudaEventRecord(c->events[(size_t)nchunks + (size_t)b], c->copy_stream));
+        } else {
+            BMX_TRY(cudaMemcpyAsync(d_text + off, src, (size_t)len, cudaMemcpyHostToDevice, c->copy_stream));
+        }
+        BMX_TRY(cudaEventRecord(c->events[(size_t)k], c->copy_stream));
+        BMX_TRY(cudaStreamWaitEvent(c->scan_stream, c->events[(size_t)k], 0));
+        // every match lying fully inside the bytes copied so far, not yet reported
+        const int64_t have = off + len;
+        const int64_t span = have - scanned;
+        if (span >= m) {
+            if ((rc = bmx_scanner_scan(c->scanner, d_text + scanned, span, scanned, c->scan_stream)) != BMX_OK) {
+                cleanup();
+                return rc;
+            }
+            scanned = have - m + 1;
+        }
+    }
+    uint64_t count = 0;
+    bmx_stats st{};
+    if ((rc = bmx_scanner_finish(c->scanner, &count, &st, c->scan_stream)) != BMX_OK) {
+        cleanup();
+        return rc;
+    }
+    *count_out = count;
+    if (stats) *stats = st;
+    const int64_t ncopy = std::min<int64_t>((int64_t)count, dev_cap);
+    if (ncopy > 0) {
+        BMX_TRY(cudaMemcpyAsync(pos_out, d_pos, (size_t)ncopy * 8, cudaMemcpyDeviceToHost, c->scan_stream));
+        BMX_TRY(cudaStreamSynchronize(c->scan_stream));
+    }
+    cleanup();
+#undef BMX_TRY
+    return BMX_OK;
+}
+
+int bmx_search(const char *text, int64_t n, const char *pat, int32_t m, int64_t *pos_out, int64_t pos_cap,
+               uint64_t *count_out)
+{
+    int device = 0;
+    if (int rc = check_device(0)) return rc;
+    BMX_CUDA(cudaGetDevice(&device));
+    return bmx_search_ex(device, text, n, pat, m, pos_out, pos_cap, count_out, BMX_VARIANT_AUTO, nullptr);
+}
+
+int bmx_search_partitions(const char *text, const char *pat, const int32_t *se, int32_t *ans, const int32_t *gs,
+                          const int32_t *bs, int32_t m, int32_t nparts)
+{
+    if (!pat || !se || !ans || nparts < 0 || (!text && nparts > 0))
+        return fail(BMX_E_BADARG, "bmx_search_partitions: NULL argument or nparts < 0");
+    if (m <= 0 || m > BMX_MAX_PATTERN)
+        return fail(BMX_E_BADARG, "pattern length %d outside 1..%d (an empty pattern is rejected)", m, BMX_MAX_PATTERN);
+    if (nparts == 0) return BMX_OK;
+
+    // The reference hands its own tables to the kernel (BoyreMoore.cpp:268-269).  The device scan
+    // keeps its own copy, so caller tables are only checked: a wrong table must not go unnoticed.
+    if (gs || bs) {
+        std::vector<int32_t> good((size_t)m);
+        int32_t bad[256];
+        build_bad_table(reinterpret_cast<const unsigned char *>(pat), m, bad);
+        build_good_table(reinterpret_cast<const unsigned char *>(pat), m, good.data());
+        if (gs)
+            for (int32_t k = 1; k < m; ++k)
+                if (gs[k] != good[(size_t)k]) return fail(BMX_E_TABLES, "gstable[%d] = %d, expected %d", k, gs[k], good[(size_t)k]);
+        if (bs)
+            for (int c = 0; c < 128; ++c)
+                if (bs[c] != bad[c]) return fail(BMX_E_TABLES, "bstable[%d] = %d, expected %d", c, bs[c], bad[c]);
+    }
+
+    int64_t lo = INT64_MAX, hi = -1;
+    for (int32_t id = 0; id < nparts; ++id) {
+        if (se[2 * id] < 0) return fail(BMX_E_BADARG, "se[%d] = %d is negative", 2 * id, se[2 * id]);
+        lo = std::min<int64_t>(lo, se[2 * id]);
+        hi = std::max<int64_t>(hi, se[2 * id + 1]);
+    }
+    for (int32_t id = 0; id < nparts; ++id) ans[id] = 0;  // kernel1.cl:6
+    const int64_t span = hi - lo + 1;
+    if (span < m) return BMX_OK;
+
+    int device = 0;
+    if (int rc = check_device(0)) return rc;
+    BMX_CUDA(cudaGetDevice(&device));
+    ThreadCtx *c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    if (int rc = ensure_streams(*c, device, 1)) return rc;
+    cudaStream_t st = c->scan_stream;
+
+    unsigned char *d_text = nullptr;
+    int64_t *d_pos = nullptr;
+    int32_t *d_se = nullptr, *d_ans = nullptr;
+    int rc = BMX_OK;
+    auto cleanup = [&]() {
+        if (d_text) cudaFreeAsync(d_text, st);
+        if (d_pos) cudaFreeAsync(d_pos, st);
+        if (d_se) cudaFreeAsync(d_se, st);
+        if (d_ans) cudaFreeAsync(d_ans, st);
+        cudaStreamSynchronize(st);
+    };
+#define BMX_TRY(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e_ = (call);                                                             \
+        if (e_ != cudaSuccess) {                                                             \
+            rc = fail(e_ == cudaErrorMemoryAllocation ? BMX_E_NOMEM : BMX_E_CUDA, "%s: %s", #call, \
+                      cudaGetErrorString(e_));                                               \
+            cleanup();                                                                       \
+            return rc;                                                                       \
+        }                                                                                    \
+    } while (0)
+    const int64_t max_hits = span - m + 1;
+    BMX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_text), (size_t)span + 16, st));
+    BMX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_pos), (size_t)max_hits * 8, st));
+    BMX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_se), (size_t)nparts * 8, st));
+    BMX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_ans), (size_t)nparts * 4, st));
+    BMX_TRY(cudaMemcpyAsync(d_text, text + lo, (size_t)span, cudaMemcpyHostToDevice, st));
+    BMX_TRY(cudaMemcpyAsync(d_se, se, (size_t)nparts * 8, cudaMemcpyHostToDevice, st));
+    if ((rc = bmx_scanner_set_pattern(c->scanner, pat, m, BMX_VARIANT_AUTO, st)) != BMX_OK ||
+        (rc = bmx_scanner_begin(c->scanner, d_pos, max_hits, st)) != BMX_OK ||
+        (rc = bmx_scanner_scan(c->scanner, d_text, span, lo, st)) != BMX_OK) {
+        cleanup();
+        return rc;
+    }
+    // the running count lives in the scanner's carry slot after one scan: slot 1
+    if ((rc = launch_partition_count(d_pos, c->scanner->d_ctrl + (c->scanner->scan_index & 1u), max_hits, d_se, d_ans, m,
+                                     nparts, st)) != BMX_OK) {
+        cleanup();
+        return rc;
+    }
+    BMX_TRY(cudaMemcpyAsync(ans, d_ans, (size_t)nparts * 4, cudaMemcpyDeviceToHost, st));
+    BMX_TRY(cudaStreamSynchronize(st));
+    cleanup();
+#undef BMX_TRY
+    return BMX_OK;
+}
+
+int bmx_synth_fill_device(void *d_text, int64_t offset, int64_t len, uint64_t seed, const unsigned char *alphabet,
+                          int32_t sigma, void *stream)
+{
+    if (len < 0 || offset < 0 || (!d_text && len > 0) || !alphabet || sigma < 1 || sigma > 256)
+        return fail(BMX_E_BADARG, "bmx_synth_fill_device: bad argument");
+    if (int rc = check_device(0)) return rc;
+    return launch_synth_fill(d_text, offset, len, seed, alphabet, sigma, stream);
+}
+
+}  // extern "C"

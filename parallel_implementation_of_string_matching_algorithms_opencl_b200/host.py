@@ -1,0 +1,198 @@
+"""Host-side mirror of the reference's interface for the Boyer-Moore path, over the C ABI.
+
+The reference has one program, BoyreMoore/BoyreMoore/BoyreMoore.cpp, whose stages map to:
+
+    build_tables(pattern)              BoyreMoore.cpp:153-190   (badSymTab / goodSymTab)
+    partition_words(text, P)           BoyreMoore.cpp:94-141    (start_endi)
+    search_partitions(text, pattern,   x64/Debug/kernel1.cl:1   (the kernel entry `search`:
+        se, gs, bs)                                              text, pattern, se, ans, gstable,
+                                                                 bstable, sublength)
+    search(text, pattern)              BoyreMoore.cpp:192-313   (buffers, launch, read-back) with
+                                                                 ONE partition {0, n-1}: the serial
+                                                                 result the north star pins parity on
+    search_device(text_cuda, pattern)  BoyreMoore.cpp:258-286   (launch + count read-back only)
+
+Everything here is a thin ctypes call into libbmx.so; there is no Python or PyTorch compute
+path and no fallback.  PyTorch appears only as the owner of device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import c_int32, c_int64, c_uint64, c_void_p
+
+import numpy as np
+
+from . import _lib
+from ._lib import BmxStats, check
+
+_VARIANTS = {"auto": 0, "qgram": 1, "window": 2, "shiftand": 3}
+
+
+def _variant(v) -> int:
+    if isinstance(v, str):
+        return _VARIANTS[v]
+    return int(v)
+
+
+def _as_bytes(pattern) -> bytes:
+    if isinstance(pattern, str):
+        return pattern.encode("latin-1")
+    return bytes(pattern)
+
+
+def version() -> int:
+    return _lib.load().bmx_version()
+
+
+def device_count() -> int:
+    return _lib.load().bmx_device_count()
+
+
+def build_tables(pattern) -> tuple[np.ndarray, np.ndarray]:
+    """(bad[256], good[m]) for `pattern` -- BoyreMoore.cpp:153-190."""
+    lib = _lib.load()
+    pat = _as_bytes(pattern)
+    m = len(pat)
+    bad = np.zeros(256, dtype=np.int32)
+    good = np.zeros(max(m, 1), dtype=np.int32)
+    check(lib.bmx_build_tables(pat, m, bad.ctypes.data_as(ctypes.POINTER(c_int32)),
+                               good.ctypes.data_as(ctypes.POINTER(c_int32))))
+    return bad, good[:m]
+
+
+def partition_words(text, nparts: int) -> np.ndarray:
+    """The reference's word partitioner -- BoyreMoore.cpp:94-141.  Returns se[2*nparts]."""
+    lib = _lib.load()
+    buf = np.frombuffer(_as_bytes(text), dtype=np.uint8)
+    se = np.zeros(2 * max(nparts, 0), dtype=np.int32)
+    check(lib.bmx_partition_words(buf.ctypes.data if buf.size else None, buf.size, nparts,
+                                  se.ctypes.data_as(ctypes.POINTER(c_int32))))
+    return se
+
+
+def _host_text(text):
+    """(pointer, n, keepalive) for bytes / numpy uint8 / CPU torch uint8 tensors."""
+    if isinstance(text, (bytes, bytearray, memoryview, str)):
+        arr = np.frombuffer(_as_bytes(text), dtype=np.uint8)
+        return (arr.ctypes.data if arr.size else None), arr.size, arr
+    if isinstance(text, np.ndarray):
+        arr = np.ascontiguousarray(text.view(np.uint8).reshape(-1))
+        return (arr.ctypes.data if arr.size else None), arr.size, arr
+    # torch CPU tensor (possibly pinned)
+    t = text.contiguous().view(-1)
+    if t.is_cuda:
+        raise TypeError("search() takes host memory; use search_device() for CUDA tensors")
+    return (t.data_ptr() if t.numel() else None), t.numel(), t
+
+
+def search(text, pattern, max_positions: int | None = None, variant="auto", device: int | None = None,
+           return_stats: bool = False):
+    """Serial-reference result for host text: (count, positions[int64]) -- BoyreMoore.cpp:192-313.
+
+    positions holds min(count, max_positions) ascending start offsets (default: room for all).
+    max_positions=0 is count-only.
+    """
+    lib = _lib.load()
+    pat = _as_bytes(pattern)
+    ptr, n, keep = _host_text(text)
+    if max_positions is None:
+        max_positions = max(n - len(pat) + 1, 0)
+    pos = np.empty(max_positions, dtype=np.int64)
+    count = c_uint64(0)
+    stats = BmxStats()
+    if device is None:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    check(lib.bmx_search_ex(device, ptr, n, pat, len(pat), pos.ctypes.data if max_positions else None,
+                            max_positions, ctypes.byref(count), _variant(variant), ctypes.byref(stats)))
+    del keep
+    out = pos[: min(count.value, max_positions)]
+    return (count.value, out, stats.as_dict()) if return_stats else (count.value, out)
+
+
+def search_device(text, pattern, pos_out=None, max_positions: int | None = None, pos_base: int = 0,
+                  variant="auto", stream=None):
+    """Scan a CUDA uint8 tensor -- BoyreMoore.cpp:258-286.  Returns (count, positions, stats).
+
+    pos_out: optional preallocated int64 CUDA tensor; otherwise max_positions (default 0 =
+    count-only) entries are allocated.  positions is the filled prefix of that tensor (or None).
+    Every reported position has pos_base added (multi-GPU shards report global offsets).
+    """
+    import torch
+
+    lib = _lib.load()
+    pat = _as_bytes(pattern)
+    if not text.is_cuda or text.dtype != torch.uint8 or not text.is_contiguous():
+        raise TypeError("search_device() needs a contiguous CUDA uint8 tensor")
+    n = text.numel()
+    with torch.cuda.device(text.device):
+        if pos_out is None and max_positions:
+            pos_out = torch.empty(int(max_positions), dtype=torch.int64, device=text.device)
+        cap = 0 if pos_out is None else pos_out.numel()
+        if pos_out is not None and (pos_out.dtype != torch.int64 or not pos_out.is_cuda or not pos_out.is_contiguous()):
+            raise TypeError("pos_out must be a contiguous CUDA int64 tensor")
+        s = stream if stream is not None else torch.cuda.current_stream(text.device)
+        count = c_uint64(0)
+        stats = BmxStats()
+        check(lib.bmx_search_device_ex(c_void_p(text.data_ptr() if n else 0), n, pat, len(pat), c_int64(pos_base),
+                                       c_void_p(pos_out.data_ptr()) if cap else None, cap, ctypes.byref(count),
+                                       _variant(variant), ctypes.byref(stats), c_void_p(s.cuda_stream)))
+    found = None if pos_out is None else pos_out[: min(count.value, cap)]
+    return count.value, found, stats.as_dict()
+
+
+def search_partitions(text, pattern, se, gs=None, bs=None) -> np.ndarray:
+    """Mirror of the kernel entry `search` (kernel1.cl:1): per-range counts ans[nparts]."""
+    lib = _lib.load()
+    pat = _as_bytes(pattern)
+    ptr, n, keep = _host_text(text)
+    se = np.ascontiguousarray(se, dtype=np.int32)
+    nparts = se.size // 2
+    if nparts and int(se[1::2].max()) >= n:
+        raise ValueError("a partition ends beyond the text")
+    ans = np.zeros(nparts, dtype=np.int32)
+    p32 = ctypes.POINTER(c_int32)
+    gs_a = None if gs is None else np.ascontiguousarray(gs, dtype=np.int32)
+    bs_a = None if bs is None else np.ascontiguousarray(bs, dtype=np.int32)
+    check(lib.bmx_search_partitions(ptr, pat, se.ctypes.data_as(p32), ans.ctypes.data_as(p32),
+                                    None if gs_a is None else gs_a.ctypes.data_as(p32),
+                                    None if bs_a is None else bs_a.ctypes.data_as(p32), len(pat), nparts))
+    del keep
+    return ans
+
+
+class Scanner:
+    """Reusable scanner (bmx_scanner_*): pattern block + look-back scratch kept across scans."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib.load()
+        self._h = c_void_p()
+        check(self._lib.bmx_scanner_create(device, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.bmx_scanner_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_pattern(self, pattern, variant="auto", stream=0):
+        pat = _as_bytes(pattern)
+        check(self._lib.bmx_scanner_set_pattern(self._h, pat, len(pat), _variant(variant), c_void_p(stream)))
+
+    def begin(self, pos_out=None, stream=0):
+        cap = 0 if pos_out is None else pos_out.numel()
+        check(self._lib.bmx_scanner_begin(self._h, c_void_p(pos_out.data_ptr()) if cap else None, cap, c_void_p(stream)))
+
+    def scan(self, text, pos_base=0, stream=0):
+        check(self._lib.bmx_scanner_scan(self._h, c_void_p(text.data_ptr()), text.numel(), c_int64(pos_base), c_void_p(stream)))
+
+    def finish(self, stream=0):
+        count = c_uint64(0)
+        stats = BmxStats()
+        check(self._lib.bmx_scanner_finish(self._h, ctypes.byref(count), ctypes.byref(stats), c_void_p(stream)))
+        return count.value, stats.as_dict()

@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the golden vectors made by
+the reference's own code and against the oracle on the same seeded inputs.  Bit-exact: identical
+count and identical ascending position list (integer/byte work, no tolerance)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import random
+
+import numpy as np
+import pytest
+
+from conftest import synth_text
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+VARIANTS_FOR = lambda m: ["auto", "window"] + (["qgram"] if m >= 7 else []) + (["shiftand"] if m <= 32 else [])  # noqa: E731
+
+
+@pytest.fixture(scope="module")
+def dev(bmx):
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    assert bmx.device_count() >= 1
+    return torch.device("cuda:0")
+
+
+def to_dev(buf, dev, misalign: int = 0):
+    """CUDA uint8 tensor holding buf, optionally starting `misalign` bytes into an allocation."""
+    a = np.frombuffer(bytes(buf), dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf
+    t = torch.empty(a.size + misalign + 64, dtype=torch.uint8, device=dev)
+    view = t[misalign: misalign + a.size]
+    if a.size:
+        view.copy_(torch.from_numpy(a.copy()))
+    return view
+
+
+def gpu_positions(bmx, text_dev, pat, variant="auto", cap=None):
+    n = text_dev.numel()
+    cap = max(n - len(pat) + 1, 1) if cap is None else cap
+    count, pos, stats = bmx.search_device(text_dev, pat, max_positions=cap, variant=variant)
+    got = pos.cpu().numpy() if pos is not None else np.zeros(0, dtype=np.int64)
+    return count, got, stats
+
+
+def test_golden_fixtures_device_and_host_paths(bmx, golden, dev):
+    """Every known-answer vector of the reference's fixtures, through both entry points."""
+    for name, pat, want, _source in golden.cases():
+        text = golden.text(name)
+        td = to_dev(text, dev)
+        for variant in VARIANTS_FOR(len(pat)):
+            count, got, _ = gpu_positions(bmx, td, pat, variant)
+            assert count == want.size and np.array_equal(got, want), (name, pat, variant)
+        count, got = bmx.search(text, pat)                       # host pointers: H2D + scan + D2H
+        assert count == want.size and np.array_equal(got, want), (name, pat, "host")
+
+
+def test_golden_synthetic_cases(bmx, golden, dev):
+    for spec, pat, want in golden.synthetic():
+        text, _ = synth_text(bmx, spec)
+        td = to_dev(text, dev)
+        for variant in VARIANTS_FOR(len(pat)):
+            count, got, _ = gpu_positions(bmx, td, pat, variant)
+            assert count == want.size and np.array_equal(got, want), (spec, variant)
+
+
+def test_device_generator_matches_host_twin(bmx, dev):
+    for name, alpha in bmx.synth.ALPHABETS.items():
+        for off, ln, mis in [(0, 4096, 0), (13, 1000, 3), (7, 1, 1), ((1 << 33) + 5, 70001, 9)]:
+            t = torch.zeros(ln + mis, dtype=torch.uint8, device=dev)[mis:]
+            bmx.synth.fill_device(t, off, 42, alpha)
+            assert np.array_equal(t.cpu().numpy(), bmx.synth.fill_host(off, ln, 42, alpha)), (name, off)
+
+
+def test_fuzz_small_alphabets_all_variants(bmx, oracle, dev):
+    """Tiny alphabets make every filter pass constantly and exercise overlap, borders and the
+    Boyer-Moore pruning of candidate bits."""
+    rnd = random.Random(1234)
+    lengths = [1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 15, 16, 17, 31, 32, 33, 64, 99, 128]
+    for it in range(260):
+        sigma = rnd.choice([1, 2, 2, 3, 4])
+        n = rnd.choice([rnd.randint(1, 300), rnd.randint(300, 70000)])
+        m = rnd.choice(lengths)
+        text = bytes(rnd.randrange(97, 97 + sigma) for _ in range(n))
+        if n >= m and rnd.random() < 0.6:
+            o = rnd.randint(0, n - m)
+            pat = text[o:o + m]
+        else:
+            pat = bytes(rnd.randrange(97, 97 + sigma) for _ in range(m))
+        want = oracle.search(text, pat)
+        td = to_dev(text, dev, misalign=rnd.randint(0, 17))
+        for variant in VARIANTS_FOR(m):
+            count, got, _ = gpu_positions(bmx, td, pat, variant)
+            assert count == want.size and np.array_equal(got, want), (it, sigma, n, m, variant)
+
+
+def test_edge_cases(bmx, oracle, dev):
+    E = bmx._lib
+    # m > n: not an error, count 0 (kernel1.cl:15,19); empty text
+    assert bmx.search(b"ab", b"abc")[0] == 0
+    assert bmx.search(b"", b"a")[0] == 0
+    c, p, _ = bmx.search_device(torch.empty(0, dtype=torch.uint8, device=dev), b"a", max_positions=4)
+    assert c == 0 and p.numel() == 0
+    # m == n, m == 1, overlapping occurrences, NUL bytes, bytes >= 0x80
+    assert list(bmx.search(b"abc", b"abc")[1]) == [0]
+    assert list(bmx.search(b"aaaa", b"aaa")[1]) == [0, 1]
+    assert list(bmx.search(b"aaaa", b"a")[1]) == [0, 1, 2, 3]
+    assert list(bmx.search(b"\x00a\x00a", b"\x00a")[1]) == [0, 2]
+    hi = bytes([200, 201, 200, 201, 200])
+    assert list(bmx.search(hi, bytes([200, 201, 200]))[1]) == [0, 2]
+    # hits at position 0 and n-m, for every variant and odd alignments
+    for m in (1, 3, 4, 7, 11, 16, 33, 128):
+        pat = bytes((i * 7 + 3) % 251 for i in range(m))
+        body = bytes(255 for _ in range(5000))
+        text = pat + body + pat
+        want = oracle.search(text, pat)
+        assert list(want) == [0, len(text) - m]
+        for mis in (0, 1, 15):
+            td = to_dev(text, dev, misalign=mis)
+            for variant in VARIANTS_FOR(m):
+                count, got, _ = gpu_positions(bmx, td, pat, variant)
+                assert np.array_equal(got, want), (m, mis, variant)
+    # empty pattern is rejected (the reference would report n+1 bogus hits)
+    with pytest.raises(bmx.BmxError) as e:
+        bmx.search(b"abc", b"")
+    assert e.value.code == E.BMX_E_BADARG
+
+
+def test_tile_seam_straddling_hits(bmx, oracle, dev):
+    """Occurrences placed across every tile boundary (16 KiB and 32 KiB tiles) and around them."""
+    n = 6 * 32768 + 777
+    rng = np.random.default_rng(5)
+    for m in (2, 4, 5, 7, 8, 11, 16, 31, 64, 128, 300):
+        text = rng.integers(0, 256, size=n, dtype=np.uint8)
+        pat = bytes(rng.integers(0, 256, size=m, dtype=np.uint8))
+        p = np.frombuffer(pat, dtype=np.uint8)
+        for seam in range(16384, n - m, 16384):
+            for delta in (-m, -m + 1, -(m // 2), -3, -1, 0, 1, 13):
+                o = seam + delta
+                if 0 <= o <= n - m:
+                    text[o:o + m] = p
+        want = oracle.search(text.tobytes(), pat)
+        for mis in (0, 5):
+            td = to_dev(text, dev, misalign=mis)
+            for variant in VARIANTS_FOR(m):
+                count, got, _ = gpu_positions(bmx, td, pat, variant)
+                assert count == want.size and np.array_equal(got, want), (m, mis, variant)
+
+
+def test_tile_size_and_pipeline_knobs(bmx, oracle, dev):
+    """Same answers for both tile sizes, shallow pipelines and one CTA per SM."""
+    text = bmx.synth.fill_host(0, 3 << 20, 77, bmx.synth.ALPHABETS["dna"])
+    pat = text[1000:1011].tobytes()
+    want = oracle.search(text.tobytes(), pat)
+    td = to_dev(text, dev)
+    old = {k: os.environ.get(k) for k in ("BMX_TILE", "BMX_STAGES", "BMX_CTAS_PER_SM")}
+    try:
+        for tile, stages, ctas in [(16384, 2, 2), (32768, 3, 2), (32768, 8, 1), (16384, 8, 1)]:
+            os.environ.update(BMX_TILE=str(tile), BMX_STAGES=str(stages), BMX_CTAS_PER_SM=str(ctas))
+            for variant in ("qgram", "window", "shiftand"):
+                count, got, stats = gpu_positions(bmx, td, pat, variant)
+                assert stats["tile_bytes"] == tile and stats["stages"] <= stages
+                assert count == want.size and np.array_equal(got, want), (tile, stages, ctas, variant)
+    finally:
+        for k, v in old.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+
+
+def test_dense_hits_and_capacity(bmx, dev):
+    """'aaaa...' / 'aaa': n-2 overlapping hits at 0..n-3; truncated output keeps the smallest."""
+    n = (1 << 20) + 123
+    td = torch.full((n,), ord("a"), dtype=torch.uint8, device=dev)
+    for variant in ("auto", "shiftand"):
+        count, pos, _ = bmx.search_device(td, b"aaa", max_positions=n, variant=variant)
+        assert count == n - 2
+        assert torch.equal(pos, torch.arange(n - 2, device=dev))
+    count, pos, _ = bmx.search_device(td, b"aaa", max_positions=1000)
+    assert count == n - 2 and torch.equal(pos, torch.arange(1000, device=dev))
+    count, pos, _ = bmx.search_device(td, b"aaa")                 # count-only: no positions buffer
+    assert count == n - 2 and pos is None
+    # periodic pattern longer than the filter: every position verifies and matches
+    count, pos, _ = bmx.search_device(td[:200000], b"a" * 64, max_positions=200000)
+    assert count == 200000 - 63 and torch.equal(pos, torch.arange(200000 - 63, device=dev))
+
+
+def test_long_patterns(bmx, oracle, dev):
+    """Patterns beyond the shared-memory limits (tables and halo fall back to global memory)."""
+    rng = np.random.default_rng(9)
+    n = 1 << 20
+    text = rng.integers(0, 4, size=n, dtype=np.uint8) + 65
+    for m in (1024, 1025, 4096, 5000, 70000):
+        o = int(rng.integers(0, n - 2 * m))
+        pat = text[o:o + m].tobytes()
+        text[o + m + 7: o + 2 * m + 7] = text[o:o + m]          # a second, adjacent copy
+        want = oracle.search(text.tobytes(), pat)
+        assert want.size >= 2
+        count, got, _ = gpu_positions(bmx, to_dev(text, dev, misalign=3), pat)
+        assert count == want.size and np.array_equal(got, want), m
+
+
+def test_pos_base_and_determinism(bmx, oracle, dev):
+    text = bmx.synth.fill_host(0, 2 << 20, 5, bmx.synth.ALPHABETS["ascii95"])
+    pat = b"the quick brown fox"
+    bmx.synth.plant_host(text, pat, bmx.synth.plant_offsets(text.size, len(pat), 300, 5))
+    want = oracle.search(text.tobytes(), pat)
+    td = to_dev(text, dev)
+    base = (1 << 40) + 12345
+    count, pos, _ = bmx.search_device(td, pat, max_positions=1000, pos_base=base)
+    assert count == want.size and np.array_equal(pos.cpu().numpy(), want + base)
+    runs = [bmx.search_device(td, pat, max_positions=1000)[1].cpu().numpy() for _ in range(5)]
+    assert all(np.array_equal(r, want) for r in runs)
+
+
+def test_partition_mirror_reproduces_reference_counts(bmx, oracle, golden):
+    """bmx_search_partitions == the kernel entry: the reference's per-process counts (1649/1642)."""
+    for name, pat, nparts, se, ans in golden.parts():
+        t = golden.text(name)
+        se2 = bmx.partition_words(t, nparts)
+        assert np.array_equal(se2, se)
+        bad, good = bmx.build_tables(pat)
+        got = bmx.search_partitions(t, pat, se2, gs=good, bs=bad[:128])   # the reference passes its tables
+        assert np.array_equal(got, ans), name
+    t = golden.text("input5L")
+    assert list(bmx.search_partitions(t, b"is", [0, 250037, 250039, 500006])) == [1649, 1642]
+    rnd = random.Random(8)
+    for _ in range(20):
+        nparts = rnd.randint(1, 10)
+        pat = rnd.choice([b"is", b"the", b"HACK", b"e", b"occurrences"])
+        se = []
+        for _p in range(nparts):
+            a = rnd.randint(0, len(t) - 2)
+            se += [a, rnd.randint(a - 1, len(t) - 1)]
+        assert np.array_equal(bmx.search_partitions(t, pat, se), oracle.search_partitions(t, pat, se)), (pat, se)
+    with pytest.raises(bmx.BmxError) as e:
+        bmx.search_partitions(t, b"is", [0, 100], gs=[0, 5])
+    assert e.value.code == bmx._lib.BMX_E_TABLES
+
+
+def test_host_path_chunked_copy(bmx, oracle):
+    """bmx_search with several H2D chunks: matches straddling chunk seams, pinned and pageable."""
+    text = bmx.synth.fill_host(0, (5 << 20) + 999, 21, bmx.synth.ALPHABETS["dna"])
+    pat = text[(1 << 20) - 5:(1 << 20) + 9].tobytes()            # straddles the first 1 MiB seam
+    want = oracle.search(text.tobytes(), pat)
+    old = os.environ.get("BMX_H2D_CHUNK_MB")
+    os.environ["BMX_H2D_CHUNK_MB"] = "1"
+    try:
+        count, got = bmx.search(text, pat)
+        assert count == want.size and np.array_equal(got, want)
+        pinned = torch.from_numpy(text.copy()).pin_memory()
+        count, got, stats = bmx.search(pinned, pat, return_stats=True)
+        assert count == want.size and np.array_equal(got, want) and stats["kernel_launches"] >= 5
+        count, got = bmx.search(pinned, pat, max_positions=0)    # count-only
+        assert count == want.size and got.size == 0
+        count, got = bmx.search(pinned, pat, max_positions=3)
+        assert count == want.size and np.array_equal(got, want[:3])
+    finally:
+        os.environ.pop("BMX_H2D_CHUNK_MB", None) if old is None else os.environ.__setitem__("BMX_H2D_CHUNK_MB", old)
+
+
+def test_scanner_chained_scans_keep_global_order(bmx, oracle, dev):
+    text = bmx.synth.fill_host(0, 1 << 20, 31, bmx.synth.ALPHABETS["dna"])
+    pat = text[5000:5008].tobytes()
+    want = oracle.search(text.tobytes(), pat)
+    td = to_dev(text, dev)
+    out = torch.empty(want.size + 10, dtype=torch.int64, device=dev)
+    s = bmx.Scanner(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    s.set_pattern(pat, stream=stream)
+    s.begin(out, stream=stream)
+    m, cut = len(pat), 333_333
+    s.scan(td[:cut], 0, stream=stream)                           # starts [0, cut-m]
+    s.scan(td[cut - m + 1:], cut - m + 1, stream=stream)         # starts [cut-m+1, n-m]
+    count, stats = s.finish(stream=stream)
+    s.close()
+    assert count == want.size and stats["kernel_launches"] == 2
+    assert np.array_equal(out[:count].cpu().numpy(), want)
+
+
+def test_abi_device_entry_point_raw(bmx, oracle, dev):
+    """bmx_search_device exactly as a C caller would use it (ctypes, raw pointers)."""
+    lib = bmx._lib.load()
+    text = bmx.synth.fill_host(0, 1 << 18, 3, bmx.synth.ALPHABETS["ascii95"])
+    pat = text[777:777 + 16].tobytes()
+    want = oracle.search(text.tobytes(), pat)
+    td = to_dev(text, dev)
+    out = torch.empty(64, dtype=torch.int64, device=dev)
+    cnt, ms = ctypes.c_uint64(), ctypes.c_float()
+    rc = lib.bmx_search_device(ctypes.c_void_p(td.data_ptr()), td.numel(), pat, len(pat), ctypes.c_void_p(out.data_ptr()),
+                               64, ctypes.byref(cnt), ctypes.byref(ms), None)
+    assert rc == 0 and cnt.value == want.size and ms.value > 0
+    assert np.array_equal(out[: cnt.value].cpu().numpy(), want)
