@@ -72,7 +72,7 @@ struct bmx_scanner {
     // result state
     unsigned long long *d_ctrl = nullptr;  // [0],[1] carry ping-pong, [2] count-only accumulator
     unsigned long long *h_result = nullptr;  // pinned
-    void *d_scratch = nullptr;  // [ticket counter 8 B][tile_state ...]
+    void *d_scratch = nullptr;  // ticket, block sums/bases, segment counts, hit masks (see bmx_scanner_scan)
     size_t d_scratch_cap = 0;
     int64_t *d_pos_out = nullptr;
     int64_t pos_cap = 0;
@@ -226,18 +226,29 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     ScanLaunch launch{};
     if (int rc = plan_scan(s->device, s->variant, s->m, s->positions, &a, &launch)) return rc;
 
-    const size_t scratch = 8 + (s->positions ? (size_t)a.num_tiles * 8 : 0);
+    // scratch: [ticket 16 B | block_sum u32 x blocks | seg_count u16 x segs]  <- zeroed per launch
+    //          [block_base u64 x blocks | mask16 u16 x chunks]                <- written before read
+    const size_t off_bsum = 16;
+    const size_t off_segc = off_bsum + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
+    const size_t zero_bytes = s->positions ? off_segc + (((size_t)a.num_segs * 2 + 15) & ~size_t(15)) : 16;
+    const size_t off_bbase = zero_bytes;
+    const size_t off_mask = off_bbase + (size_t)a.num_blocks * 8;
+    const size_t scratch = s->positions ? off_mask + (size_t)a.num_segs * kSegChunks * 2 : 16;
     if (scratch > s->d_scratch_cap) {
         BMX_CUDA(cudaStreamSynchronize(st));
         if (s->d_scratch) cudaFree(s->d_scratch);
         s->d_scratch = nullptr;
         s->d_scratch_cap = 0;
-        const size_t want = std::max<size_t>(scratch + scratch / 4, 1 << 20);
+        const size_t want = std::max<size_t>(scratch + scratch / 8, 1 << 20);
         BMX_CUDA(cudaMalloc(&s->d_scratch, want));
         s->d_scratch_cap = want;
     }
-    a.tile_counter = static_cast<uint32_t *>(s->d_scratch);
-    a.tile_state = reinterpret_cast<unsigned long long *>(static_cast<unsigned char *>(s->d_scratch) + 8);
+    unsigned char *base = static_cast<unsigned char *>(s->d_scratch);
+    a.tile_counter = reinterpret_cast<uint32_t *>(base);
+    a.block_sum = reinterpret_cast<uint32_t *>(base + off_bsum);
+    a.seg_count = reinterpret_cast<uint16_t *>(base + off_segc);
+    a.block_base = reinterpret_cast<unsigned long long *>(base + off_bbase);
+    a.mask16 = reinterpret_cast<uint16_t *>(base + off_mask);
     a.carry_in = s->d_ctrl + (s->scan_index & 1u);
     a.carry_out = s->d_ctrl + ((s->scan_index + 1u) & 1u);
     a.count_acc = s->d_ctrl + 2;
@@ -246,12 +257,14 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
         BMX_CUDA(cudaEventRecord(s->ev_start, st));
         s->timing_open = true;
     }
-    BMX_CUDA(cudaMemsetAsync(s->d_scratch, 0, scratch, st));
+    BMX_CUDA(cudaMemsetAsync(s->d_scratch, 0, zero_bytes, st));
     if (int rc = launch_scan(a, launch, s->positions, st)) return rc;
+    if (s->positions)
+        if (int rc = launch_emit(a, st)) return rc;
     BMX_CUDA(cudaEventRecord(s->ev_stop, st));
 
     s->scan_index += 1;
-    s->stats.kernel_launches += 1;
+    s->stats.kernel_launches += s->positions ? 3 : 1;
     s->stats.grid = launch.grid;
     s->stats.stages = (int32_t)a.stages;
     s->stats.tile_bytes = launch.tile_bytes;

@@ -24,10 +24,14 @@ constexpr int kPre = 16;            // bytes staged in front of a tile (q-gram o
 constexpr int kPatSmemMax = 1024;   // patterns up to this length keep pattern+tables in smem
 constexpr int kHaloSmemMax = 4096;  // longer patterns verify their tail from global memory
 
-// Tile-status word of the decoupled look-back: [63:62] state, [61:0] value.
-constexpr unsigned long long kStateAgg = 1ull << 62;    // value = hits inside this tile
-constexpr unsigned long long kStateIncl = 2ull << 62;   // value = hits in tiles 0..this
-constexpr unsigned long long kValueMask = (1ull << 62) - 1;
+// Ordered emission works on fixed units of the (16-byte aligned) text:
+//   chunk   = 16 start positions  -> one 16-bit hit mask            (mask16[v / 16])
+//   segment = 128 chunks = 2 KiB  -> one 16-bit hit count           (seg_count[v / 2048])
+//   block   = 1024 segments = 2 MiB -> one 32-bit hit count + base  (block_sum / block_base)
+constexpr int kSegBytes = 2048;
+constexpr int kSegChunks = kSegBytes / 16;   // 128
+constexpr int kBlockSegs = 1024;
+constexpr int64_t kBlockBytes = (int64_t)kSegBytes * kBlockSegs;   // 2 MiB
 
 // Kernel arguments (passed by value: they live in the constant bank of the launch).
 struct ScanArgs {
@@ -54,10 +58,16 @@ struct ScanArgs {
     // output
     int64_t *pos_out;
     int64_t pos_cap;
-    unsigned long long *tile_state;        // num_tiles words, zeroed before the launch
-    uint32_t *tile_counter;                // zeroed before the launch
+    uint32_t *tile_counter;                // ticket counter, zeroed before the launch
+    uint16_t *mask16;                      // hit mask per chunk (written only where a segment has hits)
+    uint16_t *seg_count;                   // hits per segment, zeroed before the launch
+    uint32_t *block_sum;                   // hits per block, zeroed before the launch
+    unsigned long long *block_base;        // exclusive prefix of block_sum (block-scan kernel)
+    uint32_t num_segs;
+    uint32_t num_blocks;
+    int32_t owner_offset;                  // start position of mask bit 0 relative to its chunk (-3 for QGRAM)
     const unsigned long long *carry_in;    // hits reported by earlier chained scans
-    unsigned long long *carry_out;         // carry_in + hits of this scan (written by last tile)
+    unsigned long long *carry_out;         // carry_in + hits of this scan (block-scan kernel)
     unsigned long long *count_acc;         // count-only mode: atomically accumulated
 };
 
@@ -73,6 +83,7 @@ struct ScanLaunch {
 int resolve_variant(int requested, int32_t m);
 int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *args, ScanLaunch *out);
 int launch_scan(const ScanArgs &args, const ScanLaunch &launch, bool positions, void *stream);
+int launch_emit(const ScanArgs &args, void *stream);   // block-scan + expand (positions mode)
 int launch_synth_fill(void *d_text, int64_t offset, int64_t len, uint64_t seed,
                       const unsigned char *alphabet, int32_t sigma, void *stream);
 int launch_partition_count(const int64_t *d_pos, const unsigned long long *d_count, int64_t pos_cap,

@@ -14,9 +14,14 @@
 //                   lanes holding candidates verify them right-to-left with the reference's
 //                   bad-symbol / good-suffix shifts (kernel1.cl:21-33) pruning their own
 //                   candidate bits.
-//   emission        hit masks -> warp scan -> CTA scan -> single-pass decoupled look-back over
-//                   tiles (tile order == text order) -> every hit is written at its exact rank,
-//                   so the list is ascending and bit-identical from run to run.
+//   emission        every thread holds a 16-bit hit mask per 16-byte chunk.  Warps whose 2 KiB
+//                   segment has hits store the masks (mask16) and the segment's hit count
+//                   (seg_count, block_sum); no CTA ever waits for another one.  Two small
+//                   kernels finish the job: block_scan_kernel turns the per-2-MiB block sums into
+//                   exclusive bases, expand_kernel re-derives each segment's rank by an in-block
+//                   scan and writes every hit at its exact rank with coalesced stores.  Ranks are
+//                   exact prefix sums, so the list is ascending and bit-identical from run to
+//                   run regardless of scheduling.
 //
 // Filters (bmx_variant):
 //   QGRAM    m >= 7.  Any occurrence covers the aligned 32-bit word at ceil(p/4)*4 and the word
@@ -38,7 +43,7 @@
 namespace bmx {
 
 // ---------------------------------------------------------------------------------------------
-// PTX helpers: mbarrier, 1-D TMA bulk copy, named barriers, relaxed gpu-scope accesses
+// PTX helpers: mbarrier, 1-D TMA bulk copy
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
@@ -84,37 +89,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
-// Named barrier over the consumer threads only, with an OR reduction of a predicate.
-__device__ __forceinline__ bool bar_or_consumers(int id, bool pred)
-{
-    uint32_t out;
-    asm volatile(
-        "{\n"
-        ".reg .pred pin, pout;\n"
-        "setp.ne.u32 pin, %1, 0;\n"
-        "barrier.cta.red.or.pred pout, %2, %3, pin;\n"
-        "selp.u32 %0, 1, 0, pout;\n"
-        "}\n"
-        : "=r"(out)
-        : "r"((uint32_t)pred), "r"(id), "r"(kConsumerThreads)
-        : "memory");
-    return out != 0;
-}
-__device__ __forceinline__ void bar_sync_consumers(int id)
-{
-    asm volatile("barrier.cta.sync %0, %1;" ::"r"(id), "r"(kConsumerThreads) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 // ---------------------------------------------------------------------------------------------
 // Shared-memory control block (the stages follow it, 128-byte aligned)
 // ---------------------------------------------------------------------------------------------
@@ -122,8 +96,6 @@ struct SmemCtl {
     uint64_t full[kMaxStages];     // producer -> consumers: tile bytes have landed
     uint64_t empty[kMaxStages];    // consumers -> producer: stage may be overwritten
     int32_t slot_tile[kMaxStages]; // tile index staged in each slot, -1 = no more tiles
-    uint32_t cnt[2][kConsumerWarps];          // per-warp hit counts of the current tile
-    unsigned long long base[kConsumerWarps];  // output rank of each warp's first hit
     int32_t bad[256];              // bad-symbol table   (BoyreMoore.cpp:153-162)
     uint32_t sa_mask[256];         // Shift-And occurrence masks
     int32_t good[kPatSmemMax];     // good-suffix table  (BoyreMoore.cpp:165-190)
@@ -175,48 +147,6 @@ __device__ __forceinline__ uint32_t valid_bits(int64_t p0, int64_t vmin, int64_t
     const uint32_t mlo = lo <= 0 ? 0xFFFFu : ((0xFFFFu << (int)lo) & 0xFFFFu);
     const uint32_t mhi = hi >= 15 ? 0xFFFFu : (0xFFFFu >> (15 - (int)hi));
     return mlo & mhi;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Decoupled look-back (one warp).  Returns the number of hits in tiles 0..tile-1 of this launch.
-// ---------------------------------------------------------------------------------------------
-// blocking == false: give up (return false) instead of waiting for a predecessor that has not
-// published yet; the tile then stays at "aggregate" and a later tile sums across it.
-__device__ __forceinline__ bool lookback(unsigned long long *state, uint32_t tile, unsigned long long total,
-                                         int lane, bool blocking, unsigned long long *excl_out)
-{
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_gpu(&state[0], kStateIncl | total);
-        *excl_out = 0;
-        return true;
-    }
-    if (lane == 0) st_relaxed_gpu(&state[tile], kStateAgg | total);
-    unsigned long long excl = 0;
-    int64_t idx = (int64_t)tile - 1;
-    for (;;) {
-        const int64_t my = idx - lane;
-        // the virtual tile -1 carries an inclusive prefix of zero
-        unsigned long long d = my >= 0 ? ld_relaxed_gpu(&state[my]) : kStateIncl;
-        const uint32_t st = (uint32_t)(d >> 62);
-        const uint32_t incl_mask = __ballot_sync(0xFFFFFFFFu, st == 2u);
-        const uint32_t none_mask = __ballot_sync(0xFFFFFFFFu, st == 0u);
-        const int first = incl_mask ? (__ffs(incl_mask) - 1) : 32;
-        const uint32_t relevant = first >= 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
-        if (none_mask & relevant) {
-            if (!blocking) return false;
-            __nanosleep(64);
-            continue;
-        }
-        unsigned long long v = (lane <= first) ? (d & kValueMask) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        excl += v;
-        if (first < 32) break;
-        idx -= 32;
-    }
-    if (lane == 0) st_relaxed_gpu(&state[tile], kStateIncl | (excl + total));
-    *excl_out = excl;
-    return true;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -307,10 +237,10 @@ __device__ __forceinline__ uint32_t shiftand_chunk(const uint8_t *tp, int32_t m,
 template <int VARIANT, bool FULL8, int TILE, bool POSITIONS>
 __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant__ ScanArgs A)
 {
-    constexpr int CH = TILE / (16 * kConsumerThreads);  // 16-byte chunks per thread per tile
     constexpr int WARP_BYTES = TILE / kConsumerWarps;   // contiguous bytes owned by one warp
     constexpr int OFFS = VARIANT == kQgram ? -3 : 0;    // start position of bit 0 relative to the chunk
-    static_assert(CH >= 1 && CH * 16 * kConsumerThreads == TILE, "tile must be a multiple of 4 KiB");
+    constexpr int SEGS = WARP_BYTES / kSegBytes;        // 2 KiB segments per warp per tile
+    static_assert(SEGS >= 1 && SEGS * kSegBytes * kConsumerWarps == TILE, "tile must be a multiple of 16 KiB");
 
     extern __shared__ __align__(128) uint8_t smem[];
     SmemCtl *ctl = reinterpret_cast<SmemCtl *>(smem);
@@ -399,105 +329,202 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         const int64_t tile_v0 = (int64_t)tile * TILE;
         const uint8_t *vbase = A.verify_smem ? (st - tile_v0) : A.vtext;  // text(v) = vbase[v]
 
-        uint32_t hm[CH];
-        uint32_t thread_hits = 0;
 #pragma unroll
-        for (int sl = 0; sl < CH; ++sl) {
-            const uint32_t off = warp * WARP_BYTES + sl * 512 + lane * 16;
-            const int64_t p0 = tile_v0 + off + OFFS;
-            uint32_t hits = 0;
-            if (VARIANT == kShiftAnd) {
-                hits = shiftand_chunk(st + off, A.m, ctl->sa_mask);
-                if (hits) hits &= valid_bits(p0, A.vmin, A.vmax);
-            } else {
-                const uint4 w = *reinterpret_cast<const uint4 *>(st + off);
-                uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w.x, 1);
-                if (lane == 31) w4 = *reinterpret_cast<const uint32_t *>(st + off + 16);
-                const bool any = filter_any<VARIANT, FULL8>(w, w4, A);
-                if (__ballot_sync(0xFFFFFFFFu, any)) {  // warp-uniform: most warps skip all of this
-                    if (any) {
-                        uint32_t cand = filter_mask<VARIANT, FULL8>(w, w4, A);
-                        cand &= valid_bits(p0, A.vmin, A.vmax);
-                        if (cand) hits = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good);
+        for (int sg = 0; sg < SEGS; ++sg) {
+            uint32_t hm[4];
+            uint32_t seg_hits = 0;
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+                const uint32_t off = warp * WARP_BYTES + sg * kSegBytes + sl * 512 + lane * 16;
+                const int64_t p0 = tile_v0 + off + OFFS;
+                uint32_t hits = 0;
+                if (VARIANT == kShiftAnd) {
+                    hits = shiftand_chunk(st + off, A.m, ctl->sa_mask);
+                    if (hits) hits &= valid_bits(p0, A.vmin, A.vmax);
+                } else {
+                    const uint4 w = *reinterpret_cast<const uint4 *>(st + off);
+                    uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w.x, 1);
+                    if (lane == 31) w4 = *reinterpret_cast<const uint32_t *>(st + off + 16);
+                    const bool any = filter_any<VARIANT, FULL8>(w, w4, A);
+                    if (__ballot_sync(0xFFFFFFFFu, any)) {  // warp-uniform: most warps skip all of this
+                        if (any) {
+                            uint32_t cand = filter_mask<VARIANT, FULL8>(w, w4, A);
+                            cand &= valid_bits(p0, A.vmin, A.vmax);
+                            if (cand) hits = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good);
+                        }
                     }
                 }
+                hm[sl] = hits;
+                seg_hits += __popc(hits);
             }
-            hm[sl] = hits;
-            thread_hits += __popc(hits);
+            if (!POSITIONS) {
+                my_count += seg_hits;
+            } else if (__ballot_sync(0xFFFFFFFFu, seg_hits != 0)) {
+                // this warp's segment has hits: publish its masks and its count (no waiting on anyone)
+                uint32_t total = seg_hits;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+                const uint32_t seg = (uint32_t)((tile_v0 + warp * WARP_BYTES + sg * kSegBytes) / kSegBytes);
+                uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) mk[sl * 32] = (uint16_t)hm[sl];
+                if (lane == 0) {
+                    A.seg_count[seg] = (uint16_t)total;
+                    atomicAdd(&A.block_sum[seg / kBlockSegs], total);
+                }
+            }
         }
         // every lane is done reading the stage: hand it back to the producer
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl->empty[s]);
-
-        if (!POSITIONS) {
-            my_count += thread_hits;
-            continue;
-        }
-
-        // ---- ordered emission --------------------------------------------------------------
-        const bool warp_has = __any_sync(0xFFFFFFFFu, thread_hits != 0);
-        const uint32_t buf = it & 1u;
-        uint32_t warp_total = 0;
-        if (warp_has) {
-            warp_total = thread_hits;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) warp_total += __shfl_xor_sync(0xFFFFFFFFu, warp_total, o);
-        }
-        if (lane == 0) ctl->cnt[buf][warp] = warp_total;
-        const bool tile_has = bar_or_consumers(1, warp_has);  // barrier A (also publishes cnt[])
-
-        if (warp == 0) {
-            const uint32_t c = (tile_has && lane < kConsumerWarps) ? ctl->cnt[buf][lane] : 0u;
-            uint32_t incl = c;
-#pragma unroll
-            for (int o = 1; o < kConsumerWarps; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const unsigned long long total = __shfl_sync(0xFFFFFFFFu, incl, kConsumerWarps - 1);
-            const bool last = tile == A.num_tiles - 1;
-            const bool blocking = tile_has || last || ((tile & 63u) == 63u);
-            unsigned long long excl = 0;
-            const bool known = lookback(A.tile_state, tile, total, lane, blocking, &excl);
-            if (known && (tile_has || last)) {
-                const unsigned long long carry = *A.carry_in;
-                if (tile_has && lane < kConsumerWarps) ctl->base[lane] = carry + excl + (incl - c);
-                if (last && lane == 0) *A.carry_out = carry + excl + total;
-            }
-        }
-        if (!tile_has) continue;
-        bar_sync_consumers(2);  // barrier B: base[] is ready
-        if (!warp_has) continue;
-
-        unsigned long long rank = ctl->base[warp];
-#pragma unroll
-        for (int sl = 0; sl < CH; ++sl) {
-            const uint32_t c = __popc(hm[sl]);
-            if (__ballot_sync(0xFFFFFFFFu, c != 0) == 0) continue;
-            uint32_t incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                if (lane >= o) incl += t;
-            }
-            const uint32_t slab_total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-            unsigned long long r = rank + (incl - c);
-            const int64_t p0 = tile_v0 + warp * WARP_BYTES + sl * 512 + lane * 16 + OFFS + A.pos_bias;
-            uint32_t h = hm[sl];
-            while (h) {
-                const int b = __ffs(h) - 1;
-                h &= h - 1;
-                if ((int64_t)r < A.pos_cap) A.pos_out[r] = p0 + b;
-                ++r;
-            }
-            rank += slab_total;
-        }
     }
 
     if (!POSITIONS) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my_count += __shfl_xor_sync(0xFFFFFFFFu, my_count, o);
         if (lane == 0 && my_count) atomicAdd(A.count_acc, my_count);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered emission, step 2: exclusive scan of the per-block hit counts (one CTA)
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 1024;
+
+__global__ void __launch_bounds__(kScanThreads) block_scan_kernel(const __grid_constant__ ScanArgs A)
+{
+    __shared__ unsigned long long warp_sums[kScanThreads / 32];
+    __shared__ unsigned long long running_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) running_s = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < A.num_blocks; base += kScanThreads) {
+        const uint32_t b = base + tid;
+        const unsigned long long v = b < A.num_blocks ? A.block_sum[b] : 0ull;
+        unsigned long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = warp_sums[lane];
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            warp_sums[lane] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const unsigned long long running = running_s;
+        if (b < A.num_blocks) A.block_base[b] = running + warp_sums[warp] + (incl - v);
+        __syncthreads();
+        if (tid == kScanThreads - 1) running_s = running + warp_sums[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) *A.carry_out = *A.carry_in + running_s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ordered emission, step 3: hit masks -> positions at their exact ranks (one CTA per 2 MiB block)
+// ---------------------------------------------------------------------------------------------
+constexpr int kExpandThreads = 256;
+constexpr int kExpandWarps = kExpandThreads / 32;
+constexpr int kSegsPerThread = kBlockSegs / kExpandThreads;  // 4
+constexpr uint32_t kStageThreshold = 96;  // segments with more hits go through shared memory
+
+__global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_constant__ ScanArgs A)
+{
+    const uint32_t blk = blockIdx.x;
+    if (A.block_sum[blk] == 0) return;  // sparse texts: almost every block leaves here
+
+    __shared__ uint16_t s_cnt[kBlockSegs];
+    __shared__ uint32_t s_off[kBlockSegs];
+    __shared__ uint32_t s_warp[kExpandWarps];
+    __shared__ uint16_t s_stage[kExpandWarps][kSegBytes];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    // in-block exclusive scan of the 1024 segment counts
+    uint32_t c[kSegsPerThread], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kSegsPerThread; ++j) {
+        const uint32_t seg = blk * kBlockSegs + tid * kSegsPerThread + j;
+        c[j] = seg < A.num_segs ? A.seg_count[seg] : 0u;
+        s_cnt[tid * kSegsPerThread + j] = (uint16_t)c[j];
+        sum += c[j];
+    }
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    uint32_t run = before + incl - sum;
+#pragma unroll
+    for (int j = 0; j < kSegsPerThread; ++j) {
+        s_off[tid * kSegsPerThread + j] = run;
+        run += c[j];
+    }
+    __syncthreads();
+
+    const unsigned long long rank0 = *A.carry_in + A.block_base[blk];
+    const int64_t cap = A.pos_cap;
+    // each warp owns 128 consecutive segments of the block
+    for (int s0 = warp * (kBlockSegs / kExpandWarps); s0 < (warp + 1) * (kBlockSegs / kExpandWarps); s0 += 32) {
+        uint32_t vote = __ballot_sync(0xFFFFFFFFu, s_cnt[s0 + lane] != 0);
+        while (vote) {
+            const int sl_seg = s0 + __ffs(vote) - 1;
+            vote &= vote - 1;
+            const uint32_t cnt = s_cnt[sl_seg];
+            const unsigned long long seg_rank = rank0 + s_off[sl_seg];
+            if ((int64_t)seg_rank >= cap) continue;  // truncated output keeps the smallest positions
+            const uint32_t seg = blk * kBlockSegs + sl_seg;
+            const int64_t seg_pos = (int64_t)seg * kSegBytes + A.owner_offset + A.pos_bias;
+            const uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
+            uint32_t hm[4];
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) hm[sl] = mk[sl * 32];
+            const bool staged = cnt >= kStageThreshold;
+            uint32_t done = 0;
+#pragma unroll
+            for (int sl = 0; sl < 4; ++sl) {
+                const uint32_t k = __popc(hm[sl]);
+                uint32_t in = k;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, in, o);
+                    if (lane >= o) in += t;
+                }
+                uint32_t r = done + in - k;
+                const uint32_t local0 = sl * 512 + lane * 16;
+                uint32_t h = hm[sl];
+                while (h) {
+                    const uint32_t local = local0 + __ffs(h) - 1;
+                    h &= h - 1;
+                    if (staged) {
+                        s_stage[warp][r] = (uint16_t)local;
+                    } else if ((int64_t)(seg_rank + r) < cap) {
+                        A.pos_out[seg_rank + r] = seg_pos + local;
+                    }
+                    ++r;
+                }
+                done += __shfl_sync(0xFFFFFFFFu, in, 31);
+            }
+            if (staged) {
+                __syncwarp();
+                for (uint32_t r = lane; r < cnt; r += 32)
+                    if ((int64_t)(seg_rank + r) < cap) A.pos_out[seg_rank + r] = seg_pos + s_stage[warp][r];
+                __syncwarp();
+            }
+        }
     }
 }
 
@@ -669,6 +696,9 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     out->smem_bytes = kCtlBytes + (size_t)stages * a->stage_stride;
     const int64_t tiles = (a->vlen + tile - 1) / tile;
     a->num_tiles = (uint32_t)tiles;
+    a->num_segs = (uint32_t)(tiles * (tile / kSegBytes));
+    a->num_blocks = (a->num_segs + kBlockSegs - 1) / kBlockSegs;
+    a->owner_offset = variant == BMX_VARIANT_QGRAM ? -3 : 0;
     out->grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * ctas_per_sm);
 
     const bool full8 = a->mask2 == 0xFFFFFFFFu;
@@ -688,6 +718,18 @@ int launch_scan(const ScanArgs &a, const ScanLaunch &l, bool positions, void *st
     const cudaError_t e = cudaLaunchKernel(k, dim3((unsigned)l.grid), dim3(kThreads), params, l.smem_bytes,
                                            static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail(BMX_E_CUDA, "scan kernel launch: %s", cudaGetErrorString(e));
+    return BMX_OK;
+}
+
+int launch_emit(const ScanArgs &a, void *stream)
+{
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    block_scan_kernel<<<1, kScanThreads, 0, st>>>(a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BMX_E_CUDA, "block_scan launch: %s", cudaGetErrorString(e));
+    expand_kernel<<<a.num_blocks, kExpandThreads, 0, st>>>(a);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BMX_E_CUDA, "expand launch: %s", cudaGetErrorString(e));
     return BMX_OK;
 }
 

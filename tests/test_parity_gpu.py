@@ -188,11 +188,21 @@ def test_long_patterns(bmx, oracle, dev):
     rng = np.random.default_rng(9)
     n = 1 << 20
     text = rng.integers(0, 4, size=n, dtype=np.uint8) + 65
-    for m in (1024, 1025, 4096, 5000, 70000):
-        o = int(rng.integers(0, n - 2 * m))
+
+    def find_all(hay: bytes, needle: bytes):
+        out, i = [], hay.find(needle)
+        while i >= 0:
+            out.append(i)
+            i = hay.find(needle, i + 1)
+        return np.array(out, dtype=np.int64)
+
+    for m in (1024, 1025, 2048, 4096, 5000, 70000):
+        o = int(rng.integers(0, n - 2 * m - 7))
         pat = text[o:o + m].tobytes()
         text[o + m + 7: o + 2 * m + 7] = text[o:o + m]          # a second, adjacent copy
-        want = oracle.search(text.tobytes(), pat)
+        # the oracle keeps the reference's O(m^3) table construction (BoyreMoore.cpp:165-190),
+        # which does not finish for m in the thousands: beyond 2048 the checker is bytes.find
+        want = oracle.search(text.tobytes(), pat) if m <= 2048 else find_all(text.tobytes(), pat)
         assert want.size >= 2
         count, got, _ = gpu_positions(bmx, to_dev(text, dev, misalign=3), pat)
         assert count == want.size and np.array_equal(got, want), m
@@ -248,7 +258,7 @@ def test_host_path_chunked_copy(bmx, oracle):
         assert count == want.size and np.array_equal(got, want)
         pinned = torch.from_numpy(text.copy()).pin_memory()
         count, got, stats = bmx.search(pinned, pat, return_stats=True)
-        assert count == want.size and np.array_equal(got, want) and stats["kernel_launches"] >= 5
+        assert count == want.size and np.array_equal(got, want) and stats["kernel_launches"] >= 15
         count, got = bmx.search(pinned, pat, max_positions=0)    # count-only
         assert count == want.size and got.size == 0
         count, got = bmx.search(pinned, pat, max_positions=3)
@@ -272,7 +282,7 @@ def test_scanner_chained_scans_keep_global_order(bmx, oracle, dev):
     s.scan(td[cut - m + 1:], cut - m + 1, stream=stream)         # starts [cut-m+1, n-m]
     count, stats = s.finish(stream=stream)
     s.close()
-    assert count == want.size and stats["kernel_launches"] == 2
+    assert count == want.size and stats["kernel_launches"] == 6   # 2 x (scan, block-scan, expand)
     assert np.array_equal(out[:count].cpu().numpy(), want)
 
 
