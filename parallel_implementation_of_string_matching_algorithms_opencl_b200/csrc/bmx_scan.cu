@@ -331,31 +331,49 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
 
 #pragma unroll
         for (int sg = 0; sg < SEGS; ++sg) {
-            uint32_t hm[4];
+            uint32_t hm[4] = {0u, 0u, 0u, 0u};
             uint32_t seg_hits = 0;
+            const uint32_t seg_off = warp * WARP_BYTES + sg * kSegBytes;   // this warp's 2 KiB segment
+            const int64_t seg_p0 = tile_v0 + seg_off + lane * 16 + OFFS;   // start position of bit 0, slab 0
+            if (VARIANT == kShiftAnd) {
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl) {
-                const uint32_t off = warp * WARP_BYTES + sg * kSegBytes + sl * 512 + lane * 16;
-                const int64_t p0 = tile_v0 + off + OFFS;
-                uint32_t hits = 0;
-                if (VARIANT == kShiftAnd) {
-                    hits = shiftand_chunk(st + off, A.m, ctl->sa_mask);
-                    if (hits) hits &= valid_bits(p0, A.vmin, A.vmax);
-                } else {
-                    const uint4 w = *reinterpret_cast<const uint4 *>(st + off);
-                    uint32_t w4 = __shfl_down_sync(0xFFFFFFFFu, w.x, 1);
-                    if (lane == 31) w4 = *reinterpret_cast<const uint32_t *>(st + off + 16);
-                    const bool any = filter_any<VARIANT, FULL8>(w, w4, A);
-                    if (__ballot_sync(0xFFFFFFFFu, any)) {  // warp-uniform: most warps skip all of this
-                        if (any) {
-                            uint32_t cand = filter_mask<VARIANT, FULL8>(w, w4, A);
+                for (int sl = 0; sl < 4; ++sl) {
+                    uint32_t hits = shiftand_chunk(st + seg_off + sl * 512 + lane * 16, A.m, ctl->sa_mask);
+                    if (hits) hits &= valid_bits(seg_p0 + sl * 512, A.vmin, A.vmax);
+                    hm[sl] = hits;
+                    seg_hits += __popc(hits);
+                }
+            } else {
+                // all loads of the segment first (4 x LDS.128 per lane, conflict-free), then the filter
+                const uint8_t *sp = st + seg_off;
+                uint4 w[4];
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) w[sl] = *reinterpret_cast<const uint4 *>(sp + sl * 512 + lane * 16);
+                const uint32_t after = *reinterpret_cast<const uint32_t *>(sp + kSegBytes);  // broadcast load
+                // word following each chunk: the next lane's first word; lane 31 continues in lane 0's
+                // next slab (or behind the segment), so lane 0 feeds that word into the rotation
+                uint32_t w4[4];
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    const uint32_t wrap = sl < 3 ? w[sl < 3 ? sl + 1 : 3].x : after;
+                    w4[sl] = __shfl_sync(0xFFFFFFFFu, lane == 0 ? wrap : w[sl].x, (lane + 1) & 31);
+                }
+                bool any[4];
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) any[sl] = filter_any<VARIANT, FULL8>(w[sl], w4[sl], A);
+                if (__ballot_sync(0xFFFFFFFFu, any[0] | any[1] | any[2] | any[3])) {  // warp-uniform, rare
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) {
+                        if (any[sl]) {
+                            const int64_t p0 = seg_p0 + sl * 512;
+                            uint32_t cand = filter_mask<VARIANT, FULL8>(w[sl], w4[sl], A);
                             cand &= valid_bits(p0, A.vmin, A.vmax);
-                            if (cand) hits = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good);
+                            if (cand)
+                                hm[sl] = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good);
+                            seg_hits += __popc(hm[sl]);
                         }
                     }
                 }
-                hm[sl] = hits;
-                seg_hits += __popc(hits);
             }
             if (!POSITIONS) {
                 my_count += seg_hits;
@@ -673,8 +691,8 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
         cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device) != cudaSuccess)
         return fail(BMX_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
 
-    int tile = env_int("BMX_TILE", 16384);
-    if (tile != 16384 && tile != 32768) tile = 16384;
+    int tile = env_int("BMX_TILE", 32768);   // profiles/tune_knobs.py: 32 KiB tiles, 2 CTAs/SM, 3 stages
+    if (tile != 16384 && tile != 32768) tile = 32768;
     const int ctas_per_sm = std::max(1, std::min(2, env_int("BMX_CTAS_PER_SM", 2)));
 
     // Halo: enough for the filter's look-ahead (one more word; Shift-And reads 16+m-1 bytes per

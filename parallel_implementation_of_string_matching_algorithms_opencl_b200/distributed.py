@@ -43,27 +43,21 @@ def combine_hits(count_local: int, positions_local, *, group=None, device=None, 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     device = device if device is not None else positions_local.device
-    mine = torch.tensor([int(count_local)], dtype=torch.int64, device=device)
-    total = mine.clone()
-    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)
-    counts = torch.empty(world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(counts, mine, group=group) if hasattr(dist, "all_gather_into_tensor") and device.type == "cuda" \
-        else _all_gather_list(counts, mine, group)
-    counts_host = [int(c) for c in counts.tolist()]
-    have = [min(c, 0 if positions_local is None else 1 << 62) for c in counts_host]
+    held_local = 0 if positions_local is None else int(positions_local.numel())  # may be capped below the count
+    mine = torch.tensor([int(count_local), held_local], dtype=torch.int64, device=device)
 
-    # how many positions each rank actually holds (a rank may have been capped)
-    held = torch.tensor([0 if positions_local is None else positions_local.numel()], dtype=torch.int64, device=device)
-    held_all = torch.empty(world, dtype=torch.int64, device=device)
-    _all_gather_list(held_all, held, group)
-    held_host = [int(h) for h in held_all.tolist()]
-    del have
+    total = mine[:1].clone()
+    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)          # every rank learns the global count
+    both = torch.empty(2 * world, dtype=torch.int64, device=device)
+    _all_gather_list(both, mine, group)                                  # per-rank counts and list lengths
+    both_host = both.view(world, 2).tolist()
+    counts_host = [int(c) for c, _ in both_host]
+    held_host = [int(h) for _, h in both_host]
 
     gathered = None
     if rank == dst:
         gathered = torch.empty(sum(held_host), dtype=torch.int64, device=device)
-        off = 0
-        reqs = []
+        off, reqs = 0, []
         for r in range(world):
             k = held_host[r]
             if k:
@@ -74,8 +68,8 @@ def combine_hits(count_local: int, positions_local, *, group=None, device=None, 
             off += k
         for q in reqs:
             q.wait()
-    elif held_host[rank]:
-        dist.send(positions_local[: held_host[rank]].contiguous(), dst=dst, group=group)
+    elif held_local:
+        dist.send(positions_local[:held_local].contiguous(), dst=dst, group=group)
     return int(total.item()), counts_host, gathered
 
 
