@@ -226,11 +226,12 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     ScanLaunch launch{};
     if (int rc = plan_scan(s->device, s->variant, s->m, s->positions, &a, &launch)) return rc;
 
-    // scratch: [ticket 16 B | block_sum u32 x blocks | seg_count u16 x segs]  <- zeroed per launch
+    // scratch: [ticket 16 B | block_sum u32 x blocks | seg_count u16 x segs | item_flag u8 x items]  <- zeroed per launch
     //          [block_base u64 x blocks | mask16 u16 x chunks]                <- written before read
     const size_t off_bsum = 16;
     const size_t off_segc = off_bsum + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
-    const size_t zero_bytes = s->positions ? off_segc + (((size_t)a.num_segs * 2 + 15) & ~size_t(15)) : 16;
+    const size_t off_flag = off_segc + (((size_t)a.num_segs * 2 + 15) & ~size_t(15));
+    const size_t zero_bytes = s->positions ? off_flag + (((size_t)a.num_blocks * kExpandSplit + 15) & ~size_t(15)) : 16;
     const size_t off_bbase = zero_bytes;
     const size_t off_mask = off_bbase + (size_t)a.num_blocks * 8;
     const size_t scratch = s->positions ? off_mask + (size_t)a.num_segs * kSegChunks * 2 : 16;
@@ -247,6 +248,7 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     a.tile_counter = reinterpret_cast<uint32_t *>(base);
     a.block_sum = reinterpret_cast<uint32_t *>(base + off_bsum);
     a.seg_count = reinterpret_cast<uint16_t *>(base + off_segc);
+    a.item_flag = base + off_flag;
     a.block_base = reinterpret_cast<unsigned long long *>(base + off_bbase);
     a.mask16 = reinterpret_cast<uint16_t *>(base + off_mask);
     a.carry_in = s->d_ctrl + (s->scan_index & 1u);

@@ -388,6 +388,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                 for (int sl = 0; sl < 4; ++sl) mk[sl * 32] = (uint16_t)hm[sl];
                 if (lane == 0) {
                     A.seg_count[seg] = (uint16_t)total;
+                    A.item_flag[seg / kItemSegs] = 1;   // benign race: every writer stores 1
                     atomicAdd(&A.block_sum[seg / kBlockSegs], total);
                 }
             }
@@ -455,17 +456,17 @@ constexpr int kExpandWarps = kExpandThreads / 32;
 constexpr int kSegsPerThread = kBlockSegs / kExpandThreads;  // 4
 constexpr uint32_t kStageThreshold = 96;  // segments with more hits go through shared memory
 
-__global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_constant__ ScanArgs A)
+// Work item = one eighth of a block (128 segments = 256 KiB of text).  The grid is persistent
+// (a few CTAs per SM); thread t of CTA c probes item c + t * gridDim.x, so one round of loads
+// finds all work of a sparse text, and a dense text spreads evenly over the SMs.
+
+// Emits the hits of one work item: the in-block scan of the 1024 segment counts gives every
+// segment its rank inside the block; the item's 128 segments are then expanded by the 8 warps.
+__device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, uint16_t *s_cnt, uint32_t *s_off,
+                                            uint32_t *s_warp, uint16_t *stg, int tid, int lane, int warp)
 {
-    const uint32_t blk = blockIdx.x;
-    if (A.block_sum[blk] == 0) return;  // sparse texts: almost every block leaves here
-
-    __shared__ uint16_t s_cnt[kBlockSegs];
-    __shared__ uint32_t s_off[kBlockSegs];
-    __shared__ uint32_t s_warp[kExpandWarps];
-    __shared__ uint16_t s_stage[kExpandWarps][kSegBytes];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
+    const uint32_t blk = item / kExpandSplit;
+    const uint32_t part = item % kExpandSplit;
     // in-block exclusive scan of the 1024 segment counts
     uint32_t c[kSegsPerThread], sum = 0;
 #pragma unroll
@@ -495,9 +496,10 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
 
     const unsigned long long rank0 = *A.carry_in + A.block_base[blk];
     const int64_t cap = A.pos_cap;
-    // each warp owns 128 consecutive segments of the block
-    for (int s0 = warp * (kBlockSegs / kExpandWarps); s0 < (warp + 1) * (kBlockSegs / kExpandWarps); s0 += 32) {
-        uint32_t vote = __ballot_sync(0xFFFFFFFFu, s_cnt[s0 + lane] != 0);
+    // each warp owns 16 consecutive segments of the item
+    {
+        const int s0 = part * kItemSegs + warp * (kItemSegs / kExpandWarps);
+        uint32_t vote = __ballot_sync(0xFFFFFFFFu, lane < kItemSegs / kExpandWarps && s_cnt[s0 + lane] != 0);
         while (vote) {
             const int sl_seg = s0 + __ffs(vote) - 1;
             vote &= vote - 1;
@@ -510,42 +512,92 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
             uint32_t hm[4];
 #pragma unroll
             for (int sl = 0; sl < 4; ++sl) hm[sl] = mk[sl * 32];
-            const bool staged = cnt >= kStageThreshold;
-            uint32_t done = 0;
+            // one warp scan for all four slabs: two words of two 16-bit counters each
+            uint32_t p01 = __popc(hm[0]) | (__popc(hm[1]) << 16);
+            uint32_t p23 = __popc(hm[2]) | (__popc(hm[3]) << 16);
+            const uint32_t k01 = p01, k23 = p23;
 #pragma unroll
-            for (int sl = 0; sl < 4; ++sl) {
-                const uint32_t k = __popc(hm[sl]);
-                uint32_t in = k;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, in, o);
-                    if (lane >= o) in += t;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t01 = __shfl_up_sync(0xFFFFFFFFu, p01, o);
+                const uint32_t t23 = __shfl_up_sync(0xFFFFFFFFu, p23, o);
+                if (lane >= o) {
+                    p01 += t01;
+                    p23 += t23;
                 }
-                uint32_t r = done + in - k;
-                const uint32_t local0 = sl * 512 + lane * 16;
-                uint32_t h = hm[sl];
-                while (h) {
-                    const uint32_t local = local0 + __ffs(h) - 1;
-                    h &= h - 1;
-                    if (staged) {
-                        s_stage[warp][r] = (uint16_t)local;
-                    } else if ((int64_t)(seg_rank + r) < cap) {
-                        A.pos_out[seg_rank + r] = seg_pos + local;
-                    }
-                    ++r;
-                }
-                done += __shfl_sync(0xFFFFFFFFu, in, 31);
             }
-            if (staged) {
+            const uint32_t tot01 = __shfl_sync(0xFFFFFFFFu, p01, 31), tot23 = __shfl_sync(0xFFFFFFFFu, p23, 31);
+            const uint32_t e01 = p01 - k01, e23 = p23 - k23;  // exclusive prefixes inside each slab
+            uint32_t start[4];
+            start[0] = e01 & 0xFFFFu;
+            start[1] = (tot01 & 0xFFFFu) + (e01 >> 16);
+            start[2] = (tot01 & 0xFFFFu) + (tot01 >> 16) + (e23 & 0xFFFFu);
+            start[3] = (tot01 & 0xFFFFu) + (tot01 >> 16) + (tot23 & 0xFFFFu) + (e23 >> 16);
+            const int64_t room = cap - (int64_t)seg_rank;            // > 0 here
+            const uint32_t limit = room < (int64_t)cnt ? (uint32_t)room : cnt;
+            int64_t *out = A.pos_out + seg_rank;
+            if (cnt >= kStageThreshold) {
+                // dense segment: scatter 16-bit local offsets into shared memory (XOR-swizzled so the
+                // 16 consecutive ranks of a lane do not pile up on 4 banks), then write coalesced
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    uint32_t r = start[sl];
+                    const uint32_t local0 = sl * 512 + lane * 16;
+                    uint32_t h = hm[sl];
+                    while (h) {
+                        const uint32_t bit = __ffs(h) - 1;
+                        h &= h - 1;
+                        stg[r ^ ((r >> 4) & 15u)] = (uint16_t)(local0 + bit);
+                        ++r;
+                    }
+                }
                 __syncwarp();
-                for (uint32_t r = lane; r < cnt; r += 32)
-                    if ((int64_t)(seg_rank + r) < cap) A.pos_out[seg_rank + r] = seg_pos + s_stage[warp][r];
+#pragma unroll 4
+                for (uint32_t r = lane; r < limit; r += 32) out[r] = seg_pos + stg[r ^ ((r >> 4) & 15u)];
                 __syncwarp();
+            } else {
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) {
+                    uint32_t r = start[sl];
+                    const uint32_t local0 = sl * 512 + lane * 16;
+                    uint32_t h = hm[sl];
+                    while (h) {
+                        const uint32_t bit = __ffs(h) - 1;
+                        h &= h - 1;
+                        if (r < limit) out[r] = seg_pos + local0 + bit;
+                        ++r;
+                    }
+                }
             }
         }
     }
 }
 
+__global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_constant__ ScanArgs A)
+{
+    __shared__ uint16_t s_cnt[kBlockSegs];
+    __shared__ uint32_t s_off[kBlockSegs];
+    __shared__ uint32_t s_warp[kExpandWarps];
+    __shared__ uint16_t s_stage[kExpandWarps][kSegBytes];
+    __shared__ uint32_t s_items[kExpandThreads];
+    __shared__ uint32_t s_nitems;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t items = A.num_blocks * kExpandSplit;
+
+    for (uint32_t round = 0; round * gridDim.x * kExpandThreads < items; ++round) {
+        // ---- which of this CTA's items have hits?
+        if (tid == 0) s_nitems = 0;
+        __syncthreads();
+        const uint32_t mine = round * gridDim.x * kExpandThreads + tid * gridDim.x + blockIdx.x;
+        if (mine < items && A.item_flag[mine] != 0) s_items[atomicAdd(&s_nitems, 1u)] = mine;
+        __syncthreads();
+        const uint32_t nitems = s_nitems;
+        for (uint32_t ii = 0; ii < nitems; ++ii) {
+            const uint32_t item = s_items[ii];
+            expand_item(A, item, s_cnt, s_off, s_warp, s_stage[warp], tid, lane, warp);
+            __syncthreads();
+        }
+    }
+}
 // ---------------------------------------------------------------------------------------------
 // Small utility kernels
 // ---------------------------------------------------------------------------------------------
@@ -745,7 +797,12 @@ int launch_emit(const ScanArgs &a, void *stream)
     block_scan_kernel<<<1, kScanThreads, 0, st>>>(a);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BMX_E_CUDA, "block_scan launch: %s", cudaGetErrorString(e));
-    expand_kernel<<<a.num_blocks, kExpandThreads, 0, st>>>(a);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t items = a.num_blocks * kExpandSplit;
+    const uint32_t grid = std::min<uint32_t>(items, (uint32_t)sms * 5u);  // 5 CTAs of 256 threads fit per SM
+    expand_kernel<<<grid, kExpandThreads, 0, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BMX_E_CUDA, "expand launch: %s", cudaGetErrorString(e));
     return BMX_OK;

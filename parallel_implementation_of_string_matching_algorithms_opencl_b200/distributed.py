@@ -6,9 +6,10 @@ straddle a seam (BoyreMoore.cpp:119-141).  Here rank r owns the m
 positions [lo_r, hi_r) and reads (m-1) bytes of halo behind hi_r, so every occurrence is reported
 exactly once by the rank that owns its start, with its global offset (pos_base = lo_r).
 
-Exchange step (the only collective on the path): all_reduce(sum) of the hit counts, all_gather of
-the per-rank counts, then the per-rank position lists are sent to rank 0, whose rank-order
-concatenation is already globally ascending.  Over NCCL this runs on NVLink/NVSwitch; the same
+Exchange step (the only collectives on the path): all_reduce(sum) of the hit counts and ONE
+all_gather carrying each rank's count and (the head of) its position list; rank 0 concatenates
+the lists in rank order, which is already globally ascending.  Longer lists send their tail to
+rank 0 point-to-point.  Over NCCL this runs on NVLink/NVSwitch; the same
 code runs over gloo on CPU tensors in the tests.
 """
 from __future__ import annotations
@@ -32,10 +33,20 @@ def shard_read_range(n_total: int, m: int, lo: int, hi: int) -> tuple[int, int]:
     return lo, min(n_total, hi + max(m - 1, 0))
 
 
-def combine_hits(count_local: int, positions_local, *, group=None, device=None, dst: int = 0):
+FAST_GATHER_CAP = 4096  # positions per rank that ride along with the count exchange
+
+
+def combine_hits(count_local: int, positions_local, *, group=None, device=None, dst: int = 0,
+                 fast_cap: int = FAST_GATHER_CAP):
     """Exchange step.  Returns (total_count, per_rank_counts, positions_on_dst_or_None).
 
-    positions_local: 1-D int64 tensor of this rank's GLOBAL positions (ascending), on `device`.
+    positions_local: 1-D int64 tensor of this rank's GLOBAL positions (ascending), on `device`
+    (it may hold fewer than count_local entries when the caller capped its output).
+
+    One all-gather carries every rank's [count, list length, first fast_cap positions]; the
+    all-reduce of the counts is enqueued next to it and both are awaited with a single host
+    synchronisation.  Lists longer than fast_cap (dense texts) send their remainder to `dst`
+    point-to-point.  Rank-order concatenation on `dst` is globally ascending, so nothing is sorted.
     """
     import torch
     import torch.distributed as dist
@@ -43,34 +54,49 @@ def combine_hits(count_local: int, positions_local, *, group=None, device=None, 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     device = device if device is not None else positions_local.device
-    held_local = 0 if positions_local is None else int(positions_local.numel())  # may be capped below the count
-    mine = torch.tensor([int(count_local), held_local], dtype=torch.int64, device=device)
+    held_local = 0 if positions_local is None else int(positions_local.numel())
+    width = 2 + fast_cap
+
+    mine = torch.empty(width, dtype=torch.int64, device=device)
+    mine[:2] = torch.tensor([int(count_local), held_local], dtype=torch.int64)
+    k_local = min(held_local, fast_cap)
+    if k_local:
+        mine[2: 2 + k_local] = positions_local[:k_local]
 
     total = mine[:1].clone()
-    dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group)          # every rank learns the global count
-    both = torch.empty(2 * world, dtype=torch.int64, device=device)
-    _all_gather_list(both, mine, group)                                  # per-rank counts and list lengths
-    both_host = both.view(world, 2).tolist()
-    counts_host = [int(c) for c, _ in both_host]
-    held_host = [int(h) for _, h in both_host]
+    work = dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group, async_op=True)   # global hit count
+    everyone = torch.empty(world * width, dtype=torch.int64, device=device)
+    try:
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+    except (RuntimeError, NotImplementedError):
+        _all_gather_list(everyone, mine, group)
+    work.wait()
+    table = everyone.view(world, width)
+    header = torch.cat([table[:, :2].reshape(-1), total]).cpu()        # the single host sync
+    counts_host = [int(header[2 * r]) for r in range(world)]
+    held_host = [int(header[2 * r + 1]) for r in range(world)]
+    total_host = int(header[-1])
 
     gathered = None
     if rank == dst:
         gathered = torch.empty(sum(held_host), dtype=torch.int64, device=device)
         off, reqs = 0, []
         for r in range(world):
-            k = held_host[r]
+            k = min(held_host[r], fast_cap)
             if k:
+                gathered[off: off + k] = table[r, 2: 2 + k]
+            rest = held_host[r] - k
+            if rest > 0:
                 if r == dst:
-                    gathered[off: off + k].copy_(positions_local[:k])
+                    gathered[off + k: off + k + rest] = positions_local[k: k + rest]
                 else:
-                    reqs.append(dist.irecv(gathered[off: off + k], src=r, group=group))
-            off += k
+                    reqs.append(dist.irecv(gathered[off + k: off + k + rest], src=r, group=group))
+            off += held_host[r]
         for q in reqs:
             q.wait()
-    elif held_local:
-        dist.send(positions_local[:held_local].contiguous(), dst=dst, group=group)
-    return int(total.item()), counts_host, gathered
+    elif held_local > fast_cap:
+        dist.send(positions_local[fast_cap:held_local].contiguous(), dst=dst, group=group)
+    return total_host, counts_host, gathered
 
 
 def _all_gather_list(out, mine, group):
@@ -83,7 +109,7 @@ def _all_gather_list(out, mine, group):
 
 
 def sharded_search(shard_text, lo: int, pattern: bytes, *, max_positions: int, group=None, dst: int = 0,
-                   variant="auto", local_scan: Optional[Callable] = None):
+                   variant="auto", local_scan: Optional[Callable] = None, fast_cap: int = FAST_GATHER_CAP):
     """Scan this rank's shard and run the exchange step.
 
     shard_text holds the bytes [lo, end) of the global text (own range + halo, see
@@ -98,5 +124,5 @@ def sharded_search(shard_text, lo: int, pattern: bytes, *, max_positions: int, g
             return search_device(text, pat, max_positions=cap, pos_base=pos_base, variant=variant)
 
     count, pos, stats = local_scan(shard_text, pattern, lo, max_positions)
-    total, counts, gathered = combine_hits(count, pos, group=group, device=shard_text.device, dst=dst)
+    total, counts, gathered = combine_hits(count, pos, group=group, device=shard_text.device, dst=dst, fast_cap=fast_cap)
     return total, counts, gathered, stats

@@ -24,7 +24,7 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _worker(rank: int, world: int, port: int, n_total: int, m: int, seed: int, out_dir: str):
+def _worker(rank: int, world: int, port: int, n_total: int, m: int, seed: int, out_dir: str, fast_cap: int):
     import torch.distributed as dist
 
     from conftest import load_oracle
@@ -53,7 +53,7 @@ def _worker(rank: int, world: int, port: int, n_total: int, m: int, seed: int, o
         got = oracle.search(text.numpy().tobytes(), pattern) + pos_base
         return int(got.size), torch.from_numpy(got[:cap].copy()), {"variant": "oracle"}
 
-    total, counts, gathered, _ = bd.sharded_search(torch.from_numpy(shard), lo, pat, max_positions=1 << 20,
+    total, counts, gathered, _ = bd.sharded_search(torch.from_numpy(shard), lo, pat, max_positions=1 << 20, fast_cap=fast_cap,
                                                    local_scan=oracle_scan)
     np.save(os.path.join(out_dir, f"count_{rank}.npy"), np.array([total] + counts, dtype=np.int64))
     if rank == 0:
@@ -62,12 +62,12 @@ def _worker(rank: int, world: int, port: int, n_total: int, m: int, seed: int, o
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_sharded_search_equals_serial_result(world, tmp_path, bmx, oracle):
+@pytest.mark.parametrize("world,fast_cap", [(2, 4096), (3, 4096), (2, 5)])
+def test_sharded_search_equals_serial_result(world, fast_cap, tmp_path, bmx, oracle):
     import torch.multiprocessing as mp
 
     n_total, m, seed = 300_007, 12, 77
-    mp.spawn(_worker, args=(world, _free_port(), n_total, m, seed, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), n_total, m, seed, str(tmp_path), fast_cap), nprocs=world, join=True)
 
     # serial truth over the whole text, built the same way in one piece
     from parallel_implementation_of_string_matching_algorithms_opencl_b200 import distributed as bd
