@@ -299,3 +299,25 @@ def test_abi_device_entry_point_raw(bmx, oracle, dev):
                                64, ctypes.byref(cnt), ctypes.byref(ms), None)
     assert rc == 0 and cnt.value == want.size and ms.value > 0
     assert np.array_equal(out[: cnt.value].cpu().numpy(), want)
+
+
+def test_refmain_demo_prints_the_reference_console_lines(bmx, golden, tmp_path):
+    """bmx_refmain = BoyreMoore.cpp main() on libbmx.so: same files, same lines, same counts."""
+    import re
+    import subprocess
+    from parallel_implementation_of_string_matching_algorithms_opencl_b200 import build as b
+
+    exe = bmx.LIB_PATH.parent / "bmx_refmain"
+    if not exe.exists():
+        b.build()
+    (tmp_path / "inputEd.txt").write_bytes(golden.text("input5L"))
+    (tmp_path / "input1Search.txt").write_bytes(b"is")          # the reference's own pattern file
+    out = subprocess.run([str(exe)], cwd=tmp_path, capture_output=True, timeout=300, check=True).stdout.decode("latin-1")
+    assert out.count("The no. of occurrences by process 0 is 1649") == 10     # 10 timed runs
+    assert out.count("The no. of occurrences by process 1 is 1642") == 10
+    found = [(int(i), int(p)) for i, p in re.findall(r"Found by (\d+) at : (\d+)", out)]
+    want = [p for _t, pat, p, _s in [c for c in golden.cases() if c[0] == "input5L" and c[1] == b"is"]][0]
+    assert [p for _i, p in found] == list(want)                               # all 3291, ascending
+    assert all((i == 0) == (p <= 250037) for i, p in found)                   # printed by the owning process
+    assert "Serial result (one range, (m-1)-byte halos): 3291 occurrences" in out
+    assert "Average time" in out
