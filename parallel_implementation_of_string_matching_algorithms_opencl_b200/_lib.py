@@ -5,7 +5,10 @@ import ctypes
 from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libbmx.so"
+import os
+
+# BMX_LIB points the binding at another build of the same ABI (A/B runs in profiles/); default: in-tree
+LIB_PATH = Path(os.environ.get("BMX_LIB") or Path(__file__).resolve().parent / "libbmx.so")
 
 BMX_OK = 0
 BMX_E_BADARG = -1

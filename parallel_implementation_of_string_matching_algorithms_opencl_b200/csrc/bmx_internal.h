@@ -53,6 +53,7 @@ struct ScanArgs {
     uint32_t f[4];          // QGRAM: hash of P[r..r+q) for r = 0..3; WINDOW: f[0] = target
     uint32_t mask2;         // QGRAM: mask of the second word (q-4 bytes)
     uint32_t mulc;          // WINDOW: 2^(32-8q), drops the bytes beyond q
+    uint32_t shl[3];        // WINDOW: 2^24, 2^16, 2^8 (funnel shifts done as multiplies on the FMA pipe)
     // per-pattern block in global memory
     const uint8_t *g_pat;
     const int32_t *g_bad;

@@ -154,16 +154,25 @@ __device__ __forceinline__ uint32_t valid_bits(int64_t p0, int64_t vmin, int64_t
 // ---------------------------------------------------------------------------------------------
 enum : int { kQgram = 1, kWindow = 2, kShiftAnd = 3 };
 
-template <int VARIANT, bool FULL8>
+// WINDOW: the 4-byte window that starts s bytes into `lo` (continuing in `hi`).  (Building the
+// shifted windows on the FMA pipe with IMAD.HI/IMAD instead of SHF was measured 13 % slower.)
+template <bool Q4>
+__device__ __forceinline__ uint32_t window_at(uint32_t lo, uint32_t hi, int s, const ScanArgs &)
+{
+    return s == 0 ? lo : __funnelshift_r(lo, hi, 8 * s);
+}
+
+// FLAG: QGRAM -> the second word is used in full (m >= 11); WINDOW -> q == 4 (m >= 4).
+template <int VARIANT, bool FLAG>
 __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const ScanArgs &A)
 {
     if (VARIANT == kQgram) {
         const uint32_t f0 = A.f[0], f1 = A.f[1], f2 = A.f[2], f3 = A.f[3];
         const uint32_t m2 = A.mask2;
-        const uint32_t h0 = w.x + kHashMul * (FULL8 ? w.y : (w.y & m2));
-        const uint32_t h1 = w.y + kHashMul * (FULL8 ? w.z : (w.z & m2));
-        const uint32_t h2 = w.z + kHashMul * (FULL8 ? w.w : (w.w & m2));
-        const uint32_t h3 = w.w + kHashMul * (FULL8 ? w4 : (w4 & m2));
+        const uint32_t h0 = w.x + kHashMul * (FLAG ? w.y : (w.y & m2));
+        const uint32_t h1 = w.y + kHashMul * (FLAG ? w.z : (w.z & m2));
+        const uint32_t h2 = w.z + kHashMul * (FLAG ? w.w : (w.w & m2));
+        const uint32_t h3 = w.w + kHashMul * (FLAG ? w4 : (w4 & m2));
         bool any = (h0 == f0) | (h0 == f1) | (h0 == f2) | (h0 == f3);
         any |= (h1 == f0) | (h1 == f1) | (h1 == f2) | (h1 == f3);
         any |= (h2 == f0) | (h2 == f1) | (h2 == f2) | (h2 == f3);
@@ -175,16 +184,17 @@ __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const Sc
         bool any = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            any |= (ww[j] * mc == tg);
-            any |= (__funnelshift_r(ww[j], ww[j + 1], 8) * mc == tg);
-            any |= (__funnelshift_r(ww[j], ww[j + 1], 16) * mc == tg);
-            any |= (__funnelshift_r(ww[j], ww[j + 1], 24) * mc == tg);
+#pragma unroll
+            for (int sh = 0; sh < 4; ++sh) {
+                const uint32_t x = window_at<FLAG>(ww[j], ww[j + 1], sh, A);
+                any |= FLAG ? (x == tg) : (x * mc == tg);
+            }
         }
         return any;
     }
 }
 
-template <int VARIANT, bool FULL8>
+template <int VARIANT, bool FLAG>
 __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, const ScanArgs &A)
 {
     uint32_t mask = 0;
@@ -192,7 +202,7 @@ __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, con
     if (VARIANT == kQgram) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t h = ww[j] + kHashMul * (FULL8 ? ww[j + 1] : (ww[j + 1] & A.mask2));
+            const uint32_t h = ww[j] + kHashMul * (FLAG ? ww[j + 1] : (ww[j + 1] & A.mask2));
             // word j with residue r flags start position 4j - r, i.e. bit 4j + 3 - r (bit 0 = c - 3)
 #pragma unroll
             for (int r = 0; r < 4; ++r) mask |= (uint32_t)(h == A.f[r]) << (4 * j + 3 - r);
@@ -201,9 +211,9 @@ __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, con
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
-                const uint32_t x = s == 0 ? ww[j] : __funnelshift_r(ww[j], ww[j + 1], 8 * s);
-                mask |= (uint32_t)(x * A.mulc == A.f[0]) << (4 * j + s);
+            for (int sh = 0; sh < 4; ++sh) {
+                const uint32_t x = window_at<FLAG>(ww[j], ww[j + 1], sh, A);
+                mask |= (uint32_t)(FLAG ? (x == A.f[0]) : (x * A.mulc == A.f[0])) << (4 * j + sh);
             }
         }
     }
@@ -232,6 +242,81 @@ __device__ __forceinline__ uint32_t shiftand_chunk(const uint8_t *tp, int32_t m,
         }
     }
     return hits;
+}
+
+// Loads one 2 KiB segment the way every filter wants it: 4 x LDS.128 per lane (conflict-free)
+// plus the word that follows each 16-byte chunk (next lane's first word; lane 31 continues in
+// lane 0's next slab or behind the segment, so lane 0 feeds that word into the rotation).
+__device__ __forceinline__ void load_segment(const uint8_t *sp, int lane, uint4 (&w)[4], uint32_t (&w4)[4])
+{
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) w[sl] = *reinterpret_cast<const uint4 *>(sp + sl * 512 + lane * 16);
+    const uint32_t after = *reinterpret_cast<const uint32_t *>(sp + kSegBytes);  // broadcast load
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+        const uint32_t wrap = sl < 3 ? w[sl < 3 ? sl + 1 : 3].x : after;
+        w4[sl] = __shfl_sync(0xFFFFFFFFu, lane == 0 ? wrap : w[sl].x, (lane + 1) & 31);
+    }
+}
+
+// A warp whose segment has hits publishes its masks and its count (no waiting on anyone).
+__device__ __forceinline__ void publish_segment(const ScanArgs &A, uint32_t seg, const uint32_t (&hm)[4],
+                                                uint32_t seg_hits, int lane)
+{
+    uint32_t total = seg_hits;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+    if (total != kSegBytes) {  // a full segment (every start matches) needs no masks
+        uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) mk[sl * 32] = (uint16_t)hm[sl];
+    }
+    if (lane == 0) {
+        A.seg_count[seg] = (uint16_t)total;
+        A.item_flag[seg / kItemSegs] = 1;  // benign race: every writer stores 1
+        atomicAdd(&A.block_sum[seg / kBlockSegs], total);
+    }
+}
+
+struct VerifyCtx {
+    const uint8_t *vbase, *pat;
+    const int32_t *bad, *good;
+    bool exact_filter, all_valid;
+};
+
+// Dense text (periodic worst cases: most lanes of the previous tile had hits): this warp's part of
+// a tile without the any-pass and the vote -- every lane builds its masks right away.  Kept out of
+// line so the common path of scan_kernel stays exactly the sparse filter loop.  Returns the hits
+// found (count-only mode adds them up) with bit 63 set while the text is still dense.
+template <int VARIANT, bool FLAG, int TILE, bool POSITIONS>
+__device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const uint8_t *st, int64_t tile_v0,
+                                                      VerifyCtx vc, int warp, int lane)
+{
+    constexpr int WARP_BYTES = TILE / kConsumerWarps;
+    constexpr int OFFS = VARIANT == kQgram ? -3 : 0;
+    unsigned long long found = 0;
+    bool still_dense = true;
+    for (int sg = 0; sg < WARP_BYTES / kSegBytes; ++sg) {
+        const uint32_t seg_off = warp * WARP_BYTES + sg * kSegBytes;
+        const int64_t seg_p0 = tile_v0 + seg_off + lane * 16 + OFFS;
+        uint4 w[4];
+        uint32_t w4[4], hm[4], seg_hits = 0;
+        load_segment(st + seg_off, lane, w, w4);
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+            const int64_t p0 = seg_p0 + sl * 512;
+            uint32_t cand = filter_mask<VARIANT, FLAG>(w[sl], w4[sl], A);
+            if (!vc.all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
+            hm[sl] = 0;
+            if (cand) hm[sl] = vc.exact_filter ? cand : verify_candidates(cand, vc.vbase, p0, A.m, vc.pat, vc.bad, vc.good);
+            seg_hits += __popc(hm[sl]);
+        }
+        const uint32_t hit_lanes = __ballot_sync(0xFFFFFFFFu, seg_hits != 0);
+        still_dense = __popc(hit_lanes) >= 24;
+        found += seg_hits;
+        if (POSITIONS && hit_lanes) publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
+    }
+    return found | (still_dense ? (1ull << 63) : 0ull);
 }
 
 template <int VARIANT, bool FULL8, int TILE, bool POSITIONS>
@@ -318,6 +403,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     const int32_t *good = A.pat_smem ? ctl->good : A.g_good;
     const bool exact_filter = (VARIANT == kShiftAnd) || (VARIANT == kWindow && A.m <= 4);
     unsigned long long my_count = 0;  // count-only mode
+    bool dense_mode = false;          // per warp: candidates in most lanes -> next tile takes dense_tile()
 
     for (uint32_t it = 0;; ++it) {
         const uint32_t s = it % S;
@@ -328,68 +414,58 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         const uint8_t *st = stages + (size_t)s * A.stage_stride + kPre;  // st[0] = first byte of the tile
         const int64_t tile_v0 = (int64_t)tile * TILE;
         const uint8_t *vbase = A.verify_smem ? (st - tile_v0) : A.vtext;  // text(v) = vbase[v]
+        // every start position owned by this tile may be reported (false only at the text's ends)
+        const bool all_valid = tile_v0 + OFFS >= A.vmin && tile_v0 + (TILE - 1) + OFFS <= A.vmax;
 
+        if (VARIANT != kShiftAnd && dense_mode) {
+            const VerifyCtx vc{vbase, pat, bad, good, exact_filter, all_valid};
+            const unsigned long long r = dense_tile<VARIANT, FULL8, TILE, POSITIONS>(A, st, tile_v0, vc, warp, lane);
+            dense_mode = (r >> 63) != 0;
+            if (!POSITIONS) my_count += r & ~(1ull << 63);
+        } else {
 #pragma unroll
-        for (int sg = 0; sg < SEGS; ++sg) {
-            uint32_t hm[4] = {0u, 0u, 0u, 0u};
-            uint32_t seg_hits = 0;
-            const uint32_t seg_off = warp * WARP_BYTES + sg * kSegBytes;   // this warp's 2 KiB segment
-            const int64_t seg_p0 = tile_v0 + seg_off + lane * 16 + OFFS;   // start position of bit 0, slab 0
-            if (VARIANT == kShiftAnd) {
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                    uint32_t hits = shiftand_chunk(st + seg_off + sl * 512 + lane * 16, A.m, ctl->sa_mask);
-                    if (hits) hits &= valid_bits(seg_p0 + sl * 512, A.vmin, A.vmax);
-                    hm[sl] = hits;
-                    seg_hits += __popc(hits);
-                }
-            } else {
-                // all loads of the segment first (4 x LDS.128 per lane, conflict-free), then the filter
-                const uint8_t *sp = st + seg_off;
-                uint4 w[4];
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) w[sl] = *reinterpret_cast<const uint4 *>(sp + sl * 512 + lane * 16);
-                const uint32_t after = *reinterpret_cast<const uint32_t *>(sp + kSegBytes);  // broadcast load
-                // word following each chunk: the next lane's first word; lane 31 continues in lane 0's
-                // next slab (or behind the segment), so lane 0 feeds that word into the rotation
-                uint32_t w4[4];
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                    const uint32_t wrap = sl < 3 ? w[sl < 3 ? sl + 1 : 3].x : after;
-                    w4[sl] = __shfl_sync(0xFFFFFFFFu, lane == 0 ? wrap : w[sl].x, (lane + 1) & 31);
-                }
-                bool any[4];
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) any[sl] = filter_any<VARIANT, FULL8>(w[sl], w4[sl], A);
-                if (__ballot_sync(0xFFFFFFFFu, any[0] | any[1] | any[2] | any[3])) {  // warp-uniform, rare
+            for (int sg = 0; sg < SEGS; ++sg) {
+                uint32_t hm[4] = {0u, 0u, 0u, 0u};
+                uint32_t seg_hits = 0;
+                const uint32_t seg_off = warp * WARP_BYTES + sg * kSegBytes;   // this warp's 2 KiB segment
+                const int64_t seg_p0 = tile_v0 + seg_off + lane * 16 + OFFS;   // start position of bit 0, slab 0
+                bool has_hits = false;
+                if (VARIANT == kShiftAnd) {
 #pragma unroll
                     for (int sl = 0; sl < 4; ++sl) {
-                        if (any[sl]) {
-                            const int64_t p0 = seg_p0 + sl * 512;
-                            uint32_t cand = filter_mask<VARIANT, FULL8>(w[sl], w4[sl], A);
-                            cand &= valid_bits(p0, A.vmin, A.vmax);
-                            if (cand)
-                                hm[sl] = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good);
-                            seg_hits += __popc(hm[sl]);
+                        uint32_t hits = shiftand_chunk(st + seg_off + sl * 512 + lane * 16, A.m, ctl->sa_mask);
+                        if (hits) hits &= valid_bits(seg_p0 + sl * 512, A.vmin, A.vmax);
+                        hm[sl] = hits;
+                        seg_hits += __popc(hits);
+                    }
+                    has_hits = __any_sync(0xFFFFFFFFu, seg_hits != 0);
+                } else {
+                    uint4 w[4];
+                    uint32_t w4[4];
+                    load_segment(st + seg_off, lane, w, w4);
+                    bool any[4];
+#pragma unroll
+                    for (int sl = 0; sl < 4; ++sl) any[sl] = filter_any<VARIANT, FULL8>(w[sl], w4[sl], A);
+                    const uint32_t vote = __ballot_sync(0xFFFFFFFFu, any[0] | any[1] | any[2] | any[3]);
+                    if (vote) {  // warp-uniform and rare: the common path ends at this branch
+#pragma unroll
+                        for (int sl = 0; sl < 4; ++sl) {
+                            if (any[sl]) {
+                                const int64_t p0 = seg_p0 + sl * 512;
+                                uint32_t cand = filter_mask<VARIANT, FULL8>(w[sl], w4[sl], A);
+                                if (!all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
+                                if (cand)
+                                    hm[sl] = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good);
+                                seg_hits += __popc(hm[sl]);
+                            }
                         }
+                        has_hits = __any_sync(0xFFFFFFFFu, seg_hits != 0);
+                        dense_mode = __popc(vote) >= 24;  // takes effect with the next tile
                     }
                 }
-            }
-            if (!POSITIONS) {
-                my_count += seg_hits;
-            } else if (__ballot_sync(0xFFFFFFFFu, seg_hits != 0)) {
-                // this warp's segment has hits: publish its masks and its count (no waiting on anyone)
-                uint32_t total = seg_hits;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
-                const uint32_t seg = (uint32_t)((tile_v0 + warp * WARP_BYTES + sg * kSegBytes) / kSegBytes);
-                uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) mk[sl * 32] = (uint16_t)hm[sl];
-                if (lane == 0) {
-                    A.seg_count[seg] = (uint16_t)total;
-                    A.item_flag[seg / kItemSegs] = 1;   // benign race: every writer stores 1
-                    atomicAdd(&A.block_sum[seg / kBlockSegs], total);
+                if (has_hits) {
+                    if (!POSITIONS) my_count += seg_hits;
+                    else publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
                 }
             }
         }
@@ -456,6 +532,27 @@ constexpr int kExpandWarps = kExpandThreads / 32;
 constexpr int kSegsPerThread = kBlockSegs / kExpandThreads;  // 4
 constexpr uint32_t kStageThreshold = 96;  // segments with more hits go through shared memory
 
+// Warp-cooperative store of out[0..limit) = value(r) with 16-byte vector stores: lane l writes the
+// element pairs (2l, 2l+1) + 64j of the 16-byte aligned middle part, one lane each the ragged ends.
+template <typename F>
+__device__ __forceinline__ void store_run(int64_t *out, uint32_t limit, int lane, F value)
+{
+    const uint32_t head = (uint32_t)((reinterpret_cast<uintptr_t>(out) >> 3) & 1u);  // 1: out[0] is not 16 B aligned
+    if (head && lane == 0 && limit) out[0] = value(0);
+    const uint32_t pairs = limit > head ? (limit - head) >> 1 : 0u;
+    longlong2 *out2 = reinterpret_cast<longlong2 *>(out + head);
+#pragma unroll 4
+    for (uint32_t q = lane; q < pairs; q += 32) {
+        const uint32_t r = head + 2 * q;
+        longlong2 v;
+        v.x = value(r);
+        v.y = value(r + 1);
+        out2[q] = v;
+    }
+    const uint32_t tail = head + 2 * pairs;
+    if (tail < limit && lane == 31) out[tail] = value(tail);
+}
+
 // Work item = one eighth of a block (128 segments = 256 KiB of text).  The grid is persistent
 // (a few CTAs per SM); thread t of CTA c probes item c + t * gridDim.x, so one round of loads
 // finds all work of a sparse text, and a dense text spreads evenly over the SMs.
@@ -508,6 +605,15 @@ __device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, ui
             if ((int64_t)seg_rank >= cap) continue;  // truncated output keeps the smallest positions
             const uint32_t seg = blk * kBlockSegs + sl_seg;
             const int64_t seg_pos = (int64_t)seg * kSegBytes + A.owner_offset + A.pos_bias;
+            if (cnt == kSegBytes) {
+                // every start position of the segment matches (periodic worst case, e.g. 'aaa' in
+                // 'aaaa...'): ranks are affine in the position, so the warp streams them out directly
+                const int64_t room = cap - (int64_t)seg_rank;
+                const uint32_t limit = room < (int64_t)cnt ? (uint32_t)room : cnt;
+                int64_t *out = A.pos_out + seg_rank;
+                store_run(out, limit, lane, [&](uint32_t r) { return seg_pos + (int64_t)r; });
+                continue;
+            }
             const uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
             uint32_t hm[4];
 #pragma unroll
@@ -551,8 +657,7 @@ __device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, ui
                     }
                 }
                 __syncwarp();
-#pragma unroll 4
-                for (uint32_t r = lane; r < limit; r += 32) out[r] = seg_pos + stg[r ^ ((r >> 4) & 15u)];
+                store_run(out, limit, lane, [&](uint32_t r) { return seg_pos + (int64_t)stg[r ^ ((r >> 4) & 15u)]; });
                 __syncwarp();
             } else {
 #pragma unroll
@@ -696,6 +801,9 @@ void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, Sca
     a->f[0] = a->f[1] = a->f[2] = a->f[3] = 0;
     a->mask2 = 0xFFFFFFFFu;
     a->mulc = 1u;
+    a->shl[0] = 1u << 24;   // multiplier that shifts a word right by 8 (high half) / left by 24 (low half)
+    a->shl[1] = 1u << 16;
+    a->shl[2] = 1u << 8;
     if (variant == BMX_VARIANT_QGRAM) {
         const int q = std::min(m - 3, 8);  // every residue r = 0..3 sees q pattern bytes
         const int q2 = q - 4;              // bytes taken from the second word
@@ -721,8 +829,10 @@ static const void *pick_kernel_tile(int variant, bool full8, bool positions)
         if (full8) return positions ? kernel_ptr<kQgram, true, TILE, true>() : kernel_ptr<kQgram, true, TILE, false>();
         return positions ? kernel_ptr<kQgram, false, TILE, true>() : kernel_ptr<kQgram, false, TILE, false>();
     }
-    if (variant == BMX_VARIANT_WINDOW)
-        return positions ? kernel_ptr<kWindow, true, TILE, true>() : kernel_ptr<kWindow, true, TILE, false>();
+    if (variant == BMX_VARIANT_WINDOW) {
+        if (full8) return positions ? kernel_ptr<kWindow, true, TILE, true>() : kernel_ptr<kWindow, true, TILE, false>();
+        return positions ? kernel_ptr<kWindow, false, TILE, true>() : kernel_ptr<kWindow, false, TILE, false>();
+    }
     return positions ? kernel_ptr<kShiftAnd, true, TILE, true>() : kernel_ptr<kShiftAnd, true, TILE, false>();
 }
 
@@ -771,7 +881,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     a->owner_offset = variant == BMX_VARIANT_QGRAM ? -3 : 0;
     out->grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * ctas_per_sm);
 
-    const bool full8 = a->mask2 == 0xFFFFFFFFu;
+    const bool full8 = variant == BMX_VARIANT_WINDOW ? a->mulc == 1u : a->mask2 == 0xFFFFFFFFu;
     const void *k = pick_kernel(variant, full8, tile, positions);
     if (!k) return fail(BMX_E_BADARG, "no kernel for variant %d tile %d", variant, tile);
     if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem_bytes) != cudaSuccess)
@@ -782,7 +892,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
 
 int launch_scan(const ScanArgs &a, const ScanLaunch &l, bool positions, void *stream)
 {
-    const bool full8 = a.mask2 == 0xFFFFFFFFu;
+    const bool full8 = l.variant == BMX_VARIANT_WINDOW ? a.mulc == 1u : a.mask2 == 0xFFFFFFFFu;
     const void *k = pick_kernel(l.variant, full8, l.tile_bytes, positions);
     void *params[] = {const_cast<ScanArgs *>(&a)};
     const cudaError_t e = cudaLaunchKernel(k, dim3((unsigned)l.grid), dim3(kThreads), params, l.smem_bytes,
