@@ -288,7 +288,7 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
                          "algorithmic_bytes": int(alg_bytes), "kernel": "bmx::scan_kernel"},
-            "e2e": e2e, "gpu_launches": int(args.steps) * 3, "clocks": clk.summary(), "cpu_baseline": cpu,
+            "e2e": e2e, "gpu_launches": int(args.steps) * 2, "clocks": clk.summary(), "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     scanner.close()

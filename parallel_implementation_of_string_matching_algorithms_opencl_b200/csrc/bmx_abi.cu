@@ -230,7 +230,8 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     //          [block_base u64 x blocks | mask16 u16 x chunks]                <- written before read
     const size_t off_bsum = 16;
     const size_t off_segc = off_bsum + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
-    const size_t off_flag = off_segc + (((size_t)a.num_segs * 2 + 15) & ~size_t(15));
+    // seg_count is padded to whole blocks: the expand kernel reads a block's 1024 counts with vector loads
+    const size_t off_flag = off_segc + (size_t)a.num_blocks * kBlockSegs * 2;
     const size_t zero_bytes = s->positions ? off_flag + (((size_t)a.num_blocks * kExpandSplit + 15) & ~size_t(15)) : 16;
     const size_t off_bbase = zero_bytes;
     const size_t off_mask = off_bbase + (size_t)a.num_blocks * 8;
@@ -266,7 +267,7 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     BMX_CUDA(cudaEventRecord(s->ev_stop, st));
 
     s->scan_index += 1;
-    s->stats.kernel_launches += s->positions ? 3 : 1;
+    s->stats.kernel_launches += s->positions ? 2 : 1;
     s->stats.grid = launch.grid;
     s->stats.stages = (int32_t)a.stages;
     s->stats.tile_bytes = launch.tile_bytes;

@@ -32,8 +32,8 @@ constexpr int kSegBytes = 2048;
 constexpr int kSegChunks = kSegBytes / 16;   // 128
 constexpr int kBlockSegs = 1024;
 constexpr int64_t kBlockBytes = (int64_t)kSegBytes * kBlockSegs;   // 2 MiB
-constexpr int kExpandSplit = 8;                       // expand work item = 1/8 block
-constexpr int kItemSegs = kBlockSegs / kExpandSplit;  // 128 segments = 256 KiB of text
+constexpr int kExpandSplit = 64;                      // expand work items per block
+constexpr int kItemSegs = kBlockSegs / kExpandSplit;  // 16 segments = 32 KiB of text, one warp each
 
 // Kernel arguments (passed by value: they live in the constant bank of the launch).
 struct ScanArgs {
@@ -65,7 +65,7 @@ struct ScanArgs {
     uint16_t *mask16;                      // hit mask per chunk (written only where a segment has hits)
     uint16_t *seg_count;                   // hits per segment, zeroed before the launch
     uint32_t *block_sum;                   // hits per block, zeroed before the launch
-    uint8_t *item_flag;                    // 1 if the 256 KiB work item has hits, zeroed before the launch
+    uint8_t *item_flag;                    // 1 if the 32 KiB work item has hits, zeroed before the launch
     unsigned long long *block_base;        // exclusive prefix of block_sum (block-scan kernel)
     uint32_t num_segs;
     uint32_t num_blocks;

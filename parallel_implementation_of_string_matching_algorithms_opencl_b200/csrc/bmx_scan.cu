@@ -16,10 +16,10 @@
 //                   candidate bits.
 //   emission        every thread holds a 16-bit hit mask per 16-byte chunk.  Warps whose 2 KiB
 //                   segment has hits store the masks (mask16) and the segment's hit count
-//                   (seg_count, block_sum); no CTA ever waits for another one.  Two small
-//                   kernels finish the job: block_scan_kernel turns the per-2-MiB block sums into
-//                   exclusive bases, expand_kernel re-derives each segment's rank by an in-block
-//                   scan and writes every hit at its exact rank with coalesced stores.  Ranks are
+//                   (seg_count, block_sum); no CTA ever waits for another one.  The CTA
+//                   that finishes last turns the per-2-MiB block sums into exclusive bases, and
+//                   expand_kernel (one warp per 32 KiB item) re-derives each segment's rank and
+//                   writes every hit at its exact rank with coalesced stores.  Ranks are
 //                   exact prefix sums, so the list is ascending and bit-identical from run to
 //                   run regardless of scheduling.
 //
@@ -89,6 +89,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// Barrier over the consumer threads only (the producer warp has its own life cycle).
+__device__ __forceinline__ void bar_sync_consumers()
+{
+    asm volatile("barrier.cta.sync 1, %0;" ::"r"(kConsumerThreads) : "memory");
+}
 // ---------------------------------------------------------------------------------------------
 // Shared-memory control block (the stages follow it, 128-byte aligned)
 // ---------------------------------------------------------------------------------------------
@@ -96,6 +101,9 @@ struct SmemCtl {
     uint64_t full[kMaxStages];     // producer -> consumers: tile bytes have landed
     uint64_t empty[kMaxStages];    // consumers -> producer: stage may be overwritten
     int32_t slot_tile[kMaxStages]; // tile index staged in each slot, -1 = no more tiles
+    uint32_t is_last;              // this CTA finished last: it scans the block sums
+    unsigned long long scan_warp[kConsumerWarps];
+    unsigned long long scan_running;
     int32_t bad[256];              // bad-symbol table   (BoyreMoore.cpp:153-162)
     uint32_t sa_mask[256];         // Shift-And occurrence masks
     int32_t good[kPatSmemMax];     // good-suffix table  (BoyreMoore.cpp:165-190)
@@ -478,50 +486,38 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my_count += __shfl_xor_sync(0xFFFFFFFFu, my_count, o);
         if (lane == 0 && my_count) atomicAdd(A.count_acc, my_count);
+        return;
     }
-}
 
-// ---------------------------------------------------------------------------------------------
-// Ordered emission, step 2: exclusive scan of the per-block hit counts (one CTA)
-// ---------------------------------------------------------------------------------------------
-constexpr int kScanThreads = 1024;
-
-__global__ void __launch_bounds__(kScanThreads) block_scan_kernel(const __grid_constant__ ScanArgs A)
-{
-    __shared__ unsigned long long warp_sums[kScanThreads / 32];
-    __shared__ unsigned long long running_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) running_s = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < A.num_blocks; base += kScanThreads) {
+    // ---- ordered emission, step 2 (fused): the CTA that finishes last turns the per-block hit
+    // counts into exclusive bases and the running total, so the expand kernel can start right away.
+    __threadfence();  // this CTA's counts, masks and block sums are visible before it reports in
+    bar_sync_consumers();
+    if (tid == 0) ctl->is_last = atomicAdd(A.tile_counter + 1, 1u) == gridDim.x - 1 ? 1u : 0u;
+    bar_sync_consumers();
+    if (!ctl->is_last) return;
+    __threadfence();
+    if (tid == 0) ctl->scan_running = 0;
+    bar_sync_consumers();
+    for (uint32_t base = 0; base < A.num_blocks; base += kConsumerThreads) {
         const uint32_t b = base + tid;
-        const unsigned long long v = b < A.num_blocks ? A.block_sum[b] : 0ull;
+        const unsigned long long v = b < A.num_blocks ? __ldcg(&A.block_sum[b]) : 0ull;
         unsigned long long incl = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
             if (lane >= o) incl += t;
         }
-        if (lane == 31) warp_sums[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            unsigned long long w = warp_sums[lane];
-            unsigned long long wi = w;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-                if (lane >= o) wi += t;
-            }
-            warp_sums[lane] = wi - w;  // exclusive prefix of the warp totals
-        }
-        __syncthreads();
-        const unsigned long long running = running_s;
-        if (b < A.num_blocks) A.block_base[b] = running + warp_sums[warp] + (incl - v);
-        __syncthreads();
-        if (tid == kScanThreads - 1) running_s = running + warp_sums[warp] + incl;
-        __syncthreads();
+        if (lane == 31) ctl->scan_warp[warp] = incl;
+        bar_sync_consumers();
+        unsigned long long before = ctl->scan_running;
+        for (int w = 0; w < warp; ++w) before += ctl->scan_warp[w];
+        if (b < A.num_blocks) A.block_base[b] = before + (incl - v);
+        bar_sync_consumers();
+        if (tid == kConsumerThreads - 1) ctl->scan_running = before + incl;
+        bar_sync_consumers();
     }
-    if (tid == 0) *A.carry_out = *A.carry_in + running_s;
+    if (tid == 0) *A.carry_out = *A.carry_in + ctl->scan_running;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -529,7 +525,6 @@ __global__ void __launch_bounds__(kScanThreads) block_scan_kernel(const __grid_c
 // ---------------------------------------------------------------------------------------------
 constexpr int kExpandThreads = 256;
 constexpr int kExpandWarps = kExpandThreads / 32;
-constexpr int kSegsPerThread = kBlockSegs / kExpandThreads;  // 4
 constexpr uint32_t kStageThreshold = 96;  // segments with more hits go through shared memory
 
 // Warp-cooperative store of out[0..limit) = value(r) with 16-byte vector stores: lane l writes the
@@ -553,156 +548,143 @@ __device__ __forceinline__ void store_run(int64_t *out, uint32_t limit, int lane
     if (tail < limit && lane == 31) out[tail] = value(tail);
 }
 
-// Work item = one eighth of a block (128 segments = 256 KiB of text).  The grid is persistent
-// (a few CTAs per SM); thread t of CTA c probes item c + t * gridDim.x, so one round of loads
-// finds all work of a sparse text, and a dense text spreads evenly over the SMs.
-
-// Emits the hits of one work item: the in-block scan of the 1024 segment counts gives every
-// segment its rank inside the block; the item's 128 segments are then expanded by the 8 warps.
-__device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, uint16_t *s_cnt, uint32_t *s_off,
-                                            uint32_t *s_warp, uint16_t *stg, int tid, int lane, int warp)
+// Work item = 16 segments = 32 KiB of text, expanded by ONE warp (no block-wide barriers):
+//   rank of the item = carry + block base + hits of the block's segments in front of it (the warp
+//   sums up to 1024 16-bit counts with 4 x LDG.128 per lane), then a 16-lane scan ranks its segments.
+// Lane l of warp g probes the flag of item (32*round + l) * #warps + g, so one round of loads finds
+// all work of a sparse text (every flagged item gets its own warp), and a dense text spreads evenly.
+__device__ __forceinline__ void expand_segment(const ScanArgs &A, uint32_t seg, uint32_t cnt, unsigned long long seg_rank,
+                                               uint16_t *stg, int lane)
 {
-    const uint32_t blk = item / kExpandSplit;
-    const uint32_t part = item % kExpandSplit;
-    // in-block exclusive scan of the 1024 segment counts
-    uint32_t c[kSegsPerThread], sum = 0;
-#pragma unroll
-    for (int j = 0; j < kSegsPerThread; ++j) {
-        const uint32_t seg = blk * kBlockSegs + tid * kSegsPerThread + j;
-        c[j] = seg < A.num_segs ? A.seg_count[seg] : 0u;
-        s_cnt[tid * kSegsPerThread + j] = (uint16_t)c[j];
-        sum += c[j];
+    const int64_t cap = A.pos_cap;
+    if ((int64_t)seg_rank >= cap) return;  // truncated output keeps the smallest positions
+    const int64_t seg_pos = (int64_t)seg * kSegBytes + A.owner_offset + A.pos_bias;
+    const int64_t room = cap - (int64_t)seg_rank;  // > 0 here
+    const uint32_t limit = room < (int64_t)cnt ? (uint32_t)room : cnt;
+    int64_t *out = A.pos_out + seg_rank;
+    if (cnt == kSegBytes) {
+        // every start position of the segment matches (periodic worst case, e.g. 'aaa' in
+        // 'aaaa...'): ranks are affine in the position, so the warp streams them out directly
+        store_run(out, limit, lane, [&](uint32_t r) { return seg_pos + (int64_t)r; });
+        return;
     }
-    uint32_t incl = sum;
+    const uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
+    uint32_t hm[4];
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) hm[sl] = mk[sl * 32];
+    // one warp scan for all four slabs: two words of two 16-bit counters each
+    uint32_t p01 = __popc(hm[0]) | (__popc(hm[1]) << 16);
+    uint32_t p23 = __popc(hm[2]) | (__popc(hm[3]) << 16);
+    const uint32_t k01 = p01, k23 = p23;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t01 = __shfl_up_sync(0xFFFFFFFFu, p01, o);
+        const uint32_t t23 = __shfl_up_sync(0xFFFFFFFFu, p23, o);
+        if (lane >= o) {
+            p01 += t01;
+            p23 += t23;
+        }
+    }
+    const uint32_t tot01 = __shfl_sync(0xFFFFFFFFu, p01, 31), tot23 = __shfl_sync(0xFFFFFFFFu, p23, 31);
+    const uint32_t e01 = p01 - k01, e23 = p23 - k23;  // exclusive prefixes inside each slab
+    uint32_t start[4];
+    start[0] = e01 & 0xFFFFu;
+    start[1] = (tot01 & 0xFFFFu) + (e01 >> 16);
+    start[2] = (tot01 & 0xFFFFu) + (tot01 >> 16) + (e23 & 0xFFFFu);
+    start[3] = (tot01 & 0xFFFFu) + (tot01 >> 16) + (tot23 & 0xFFFFu) + (e23 >> 16);
+    if (cnt >= kStageThreshold) {
+        // dense segment: scatter 16-bit local offsets into shared memory (XOR-swizzled so the
+        // 16 consecutive ranks of a lane do not pile up on 4 banks), then write coalesced
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+            uint32_t r = start[sl];
+            const uint32_t local0 = sl * 512 + lane * 16;
+            uint32_t h = hm[sl];
+            while (h) {
+                const uint32_t bit = __ffs(h) - 1;
+                h &= h - 1;
+                stg[r ^ ((r >> 4) & 15u)] = (uint16_t)(local0 + bit);
+                ++r;
+            }
+        }
+        __syncwarp();
+        store_run(out, limit, lane, [&](uint32_t r) { return seg_pos + (int64_t)stg[r ^ ((r >> 4) & 15u)]; });
+        __syncwarp();
+    } else {
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+            uint32_t r = start[sl];
+            const uint32_t local0 = sl * 512 + lane * 16;
+            uint32_t h = hm[sl];
+            while (h) {
+                const uint32_t bit = __ffs(h) - 1;
+                h &= h - 1;
+                if (r < limit) out[r] = seg_pos + local0 + bit;
+                ++r;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, unsigned long long carry, uint16_t *stg, int lane)
+{
+    const uint32_t blk = item / kExpandSplit;
+    const uint32_t first = (item % kExpandSplit) * kItemSegs;  // first segment of the item inside its block
+    // hits of the block's segments in front of this item: lane l covers counts [32l, 32l+32)
+    const uint32_t blk_seg0 = blk * kBlockSegs;
+    uint32_t acc = 0;
+    if ((uint32_t)lane * 32u < first) {
+        const uint4 *cp = reinterpret_cast<const uint4 *>(A.seg_count + blk_seg0 + lane * 32);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = cp[q];  // 8 counts; pairs share a word and stay below 2^16 when summed 16 at a time
+            const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                if ((uint32_t)lane * 32u + q * 8u + j * 2u < first) acc += ws[j];
+        }
+    }
+    uint32_t before = (acc & 0xFFFFu) + (acc >> 16);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xFFFFFFFFu, before, o);
+
+    const uint32_t seg0 = blk_seg0 + first;
+    const uint32_t c = (lane < kItemSegs && seg0 + lane < A.num_segs) ? A.seg_count[seg0 + lane] : 0u;
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < kItemSegs; o <<= 1) {
         const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    uint32_t before = 0;
-    for (int w = 0; w < warp; ++w) before += s_warp[w];
-    uint32_t run = before + incl - sum;
-#pragma unroll
-    for (int j = 0; j < kSegsPerThread; ++j) {
-        s_off[tid * kSegsPerThread + j] = run;
-        run += c[j];
-    }
-    __syncthreads();
-
-    const unsigned long long rank0 = *A.carry_in + A.block_base[blk];
-    const int64_t cap = A.pos_cap;
-    // each warp owns 16 consecutive segments of the item
-    {
-        const int s0 = part * kItemSegs + warp * (kItemSegs / kExpandWarps);
-        uint32_t vote = __ballot_sync(0xFFFFFFFFu, lane < kItemSegs / kExpandWarps && s_cnt[s0 + lane] != 0);
-        while (vote) {
-            const int sl_seg = s0 + __ffs(vote) - 1;
-            vote &= vote - 1;
-            const uint32_t cnt = s_cnt[sl_seg];
-            const unsigned long long seg_rank = rank0 + s_off[sl_seg];
-            if ((int64_t)seg_rank >= cap) continue;  // truncated output keeps the smallest positions
-            const uint32_t seg = blk * kBlockSegs + sl_seg;
-            const int64_t seg_pos = (int64_t)seg * kSegBytes + A.owner_offset + A.pos_bias;
-            if (cnt == kSegBytes) {
-                // every start position of the segment matches (periodic worst case, e.g. 'aaa' in
-                // 'aaaa...'): ranks are affine in the position, so the warp streams them out directly
-                const int64_t room = cap - (int64_t)seg_rank;
-                const uint32_t limit = room < (int64_t)cnt ? (uint32_t)room : cnt;
-                int64_t *out = A.pos_out + seg_rank;
-                store_run(out, limit, lane, [&](uint32_t r) { return seg_pos + (int64_t)r; });
-                continue;
-            }
-            const uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
-            uint32_t hm[4];
-#pragma unroll
-            for (int sl = 0; sl < 4; ++sl) hm[sl] = mk[sl * 32];
-            // one warp scan for all four slabs: two words of two 16-bit counters each
-            uint32_t p01 = __popc(hm[0]) | (__popc(hm[1]) << 16);
-            uint32_t p23 = __popc(hm[2]) | (__popc(hm[3]) << 16);
-            const uint32_t k01 = p01, k23 = p23;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t01 = __shfl_up_sync(0xFFFFFFFFu, p01, o);
-                const uint32_t t23 = __shfl_up_sync(0xFFFFFFFFu, p23, o);
-                if (lane >= o) {
-                    p01 += t01;
-                    p23 += t23;
-                }
-            }
-            const uint32_t tot01 = __shfl_sync(0xFFFFFFFFu, p01, 31), tot23 = __shfl_sync(0xFFFFFFFFu, p23, 31);
-            const uint32_t e01 = p01 - k01, e23 = p23 - k23;  // exclusive prefixes inside each slab
-            uint32_t start[4];
-            start[0] = e01 & 0xFFFFu;
-            start[1] = (tot01 & 0xFFFFu) + (e01 >> 16);
-            start[2] = (tot01 & 0xFFFFu) + (tot01 >> 16) + (e23 & 0xFFFFu);
-            start[3] = (tot01 & 0xFFFFu) + (tot01 >> 16) + (tot23 & 0xFFFFu) + (e23 >> 16);
-            const int64_t room = cap - (int64_t)seg_rank;            // > 0 here
-            const uint32_t limit = room < (int64_t)cnt ? (uint32_t)room : cnt;
-            int64_t *out = A.pos_out + seg_rank;
-            if (cnt >= kStageThreshold) {
-                // dense segment: scatter 16-bit local offsets into shared memory (XOR-swizzled so the
-                // 16 consecutive ranks of a lane do not pile up on 4 banks), then write coalesced
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                    uint32_t r = start[sl];
-                    const uint32_t local0 = sl * 512 + lane * 16;
-                    uint32_t h = hm[sl];
-                    while (h) {
-                        const uint32_t bit = __ffs(h) - 1;
-                        h &= h - 1;
-                        stg[r ^ ((r >> 4) & 15u)] = (uint16_t)(local0 + bit);
-                        ++r;
-                    }
-                }
-                __syncwarp();
-                store_run(out, limit, lane, [&](uint32_t r) { return seg_pos + (int64_t)stg[r ^ ((r >> 4) & 15u)]; });
-                __syncwarp();
-            } else {
-#pragma unroll
-                for (int sl = 0; sl < 4; ++sl) {
-                    uint32_t r = start[sl];
-                    const uint32_t local0 = sl * 512 + lane * 16;
-                    uint32_t h = hm[sl];
-                    while (h) {
-                        const uint32_t bit = __ffs(h) - 1;
-                        h &= h - 1;
-                        if (r < limit) out[r] = seg_pos + local0 + bit;
-                        ++r;
-                    }
-                }
-            }
-        }
+    const unsigned long long item_rank = carry + A.block_base[blk] + before;
+    uint32_t vote = __ballot_sync(0xFFFFFFFFu, c != 0);
+    while (vote) {
+        const int src = __ffs(vote) - 1;
+        vote &= vote - 1;
+        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, c, src);
+        const uint32_t off = __shfl_sync(0xFFFFFFFFu, incl - c, src);
+        expand_segment(A, seg0 + src, cnt, item_rank + off, stg, lane);
     }
 }
 
 __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_constant__ ScanArgs A)
 {
-    __shared__ uint16_t s_cnt[kBlockSegs];
-    __shared__ uint32_t s_off[kBlockSegs];
-    __shared__ uint32_t s_warp[kExpandWarps];
     __shared__ uint16_t s_stage[kExpandWarps][kSegBytes];
-    __shared__ uint32_t s_items[kExpandThreads];
-    __shared__ uint32_t s_nitems;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t gw = blockIdx.x * kExpandWarps + warp, nw = gridDim.x * kExpandWarps;
     const uint32_t items = A.num_blocks * kExpandSplit;
-
-    for (uint32_t round = 0; round * gridDim.x * kExpandThreads < items; ++round) {
-        // ---- which of this CTA's items have hits?
-        if (tid == 0) s_nitems = 0;
-        __syncthreads();
-        const uint32_t mine = round * gridDim.x * kExpandThreads + tid * gridDim.x + blockIdx.x;
-        if (mine < items && A.item_flag[mine] != 0) s_items[atomicAdd(&s_nitems, 1u)] = mine;
-        __syncthreads();
-        const uint32_t nitems = s_nitems;
-        for (uint32_t ii = 0; ii < nitems; ++ii) {
-            const uint32_t item = s_items[ii];
-            expand_item(A, item, s_cnt, s_off, s_warp, s_stage[warp], tid, lane, warp);
-            __syncthreads();
+    const unsigned long long carry = *A.carry_in;
+    for (uint32_t base = 0; base < items; base += nw * 32u) {
+        const uint32_t mine = base + (uint32_t)lane * nw + gw;
+        uint32_t vote = __ballot_sync(0xFFFFFFFFu, mine < items && A.item_flag[mine] != 0);
+        while (vote) {
+            const int src = __ffs(vote) - 1;
+            vote &= vote - 1;
+            expand_item(A, __shfl_sync(0xFFFFFFFFu, mine, src), carry, s_stage[warp], lane);
         }
     }
 }
+
 // ---------------------------------------------------------------------------------------------
 // Small utility kernels
 // ---------------------------------------------------------------------------------------------
@@ -904,14 +886,12 @@ int launch_scan(const ScanArgs &a, const ScanLaunch &l, bool positions, void *st
 int launch_emit(const ScanArgs &a, void *stream)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    block_scan_kernel<<<1, kScanThreads, 0, st>>>(a);
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(BMX_E_CUDA, "block_scan launch: %s", cudaGetErrorString(e));
+    cudaError_t e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t items = a.num_blocks * kExpandSplit;
-    const uint32_t grid = std::min<uint32_t>(items, (uint32_t)sms * 5u);  // 5 CTAs of 256 threads fit per SM
+    const uint32_t grid = std::min<uint32_t>((items + kExpandWarps - 1) / kExpandWarps, (uint32_t)sms * 5u);  // one warp per item
     expand_kernel<<<grid, kExpandThreads, 0, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BMX_E_CUDA, "expand launch: %s", cudaGetErrorString(e));
