@@ -203,17 +203,21 @@ def run_ours(args):
         dist.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    per_step = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clk:
         e0.record()
         last = None
-        for _ in range(args.steps):
+        for a, b in per_step:
+            a.record()
             last = step()
+            b.record()
         e1.record()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-    count, stats = scanner.finish(stream=stream)
+    count, stats = scanner.finish(stream=stream)      # stats.scan_kernel_ms: the last timed step's scan kernel
     ms_total = e0.elapsed_time(e1)
+    step_gpu_ms = float(np.mean([a.elapsed_time(b) for a, b in per_step]))   # memset + scan + expand (+ exchange)
     total_hits = count
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -223,20 +227,20 @@ def run_ours(args):
     ms_step = ms_total / args.steps
     value = total_n / (ms_step * 1e-3) / 1e9
 
-    # kernel-only duration for the roofline: the scan alone (no collectives), CUDA events
-    torch.cuda.synchronize()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kreps = max(3, min(args.steps, 20))
-    k0.record()
-    for _ in range(kreps):
-        scanner.begin(pos, stream=stream)
-        scanner.scan(text, lo, stream=stream)
-    k1.record()
-    torch.cuda.synchronize()
-    kernel_ms = k0.elapsed_time(k1) / kreps
+    # roofline of the dominant kernel (scan_kernel; expand_kernel when the text is dense): CUDA events
+    # recorded by the library on the launching stream around that kernel, inside the timed region
     peak, peak_src = peaks()
-    alg_bytes = (end - lo) + 8 * min(count, cap)
+    dense_text = dense
+    kernel_ms = (step_gpu_ms - stats["scan_kernel_ms"]) if dense_text else stats["scan_kernel_ms"]
+    alg_bytes = (8 * min(count, cap) + (end - lo) // 8) if dense_text else (end - lo)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    step_bytes = (end - lo) + 8 * min(count, cap)
+    traffic = None
+    tf = ROOT / "profiles" / "r01_traffic.json"
+    if tf.exists():
+        rec = json.loads(tf.read_text()).get(name)
+        if rec and not args.bytes_per_gpu:
+            traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
 
     # ---- e2e: host-pointer C-ABI call, pinned host text, H2D + scan + D2H inside the timed region
     e2e = None
@@ -286,8 +290,11 @@ def run_ours(args):
                        "grid": stats["grid"], "l2": "inputs larger than L2 (no flush needed)" if w["n"] > (256 << 20) else "input fits L2: flushless, see DESIGN.md",
                        "verified": bool(ok), "parallelism": f"shard{world}" if world > 1 else "single"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes": int(alg_bytes), "kernel": "bmx::scan_kernel"},
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
+                         "algorithmic_bytes": int(alg_bytes), "kernel": "bmx::expand_kernel" if dense_text else "bmx::scan_kernel",
+                         "step_gpu_ms": step_gpu_ms, "step_algorithmic_bytes": int(step_bytes),
+                         "step_achieved": step_bytes / (step_gpu_ms * 1e-3) / 1e9,
+                         "step_frac": step_bytes / (step_gpu_ms * 1e-3) / 1e9 / peak},
             "e2e": e2e, "gpu_launches": int(args.steps) * 2, "clocks": clk.summary(), "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -61,6 +61,8 @@ typedef struct bmx_stats {
     int32_t tile_bytes;    /* text bytes per tile */
     int32_t smem_bytes;    /* dynamic shared memory per CTA */
     int64_t tiles;         /* tiles scanned */
+    float scan_kernel_ms;  /* CUDA-event time of the (last) scan kernel alone */
+    int32_t reserved;
 } bmx_stats;
 
 int bmx_version(void);

@@ -42,6 +42,8 @@ class BmxStats(ctypes.Structure):
         ("tile_bytes", c_int32),
         ("smem_bytes", c_int32),
         ("tiles", c_int64),
+        ("scan_kernel_ms", c_float),
+        ("reserved", c_int32),
     ]
 
     def as_dict(self) -> dict:

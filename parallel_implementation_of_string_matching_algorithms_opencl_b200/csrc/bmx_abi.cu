@@ -79,6 +79,7 @@ struct bmx_scanner {
     bool positions = false;
     uint32_t scan_index = 0;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the scan kernel alone
     bool timing_open = false;
     bmx_stats stats{};
 };
@@ -121,6 +122,8 @@ int bmx_scanner_create(int device, bmx_scanner **out)
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_result, 64, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_stop);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_k0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev_k1);
     if (e != cudaSuccess) {
         bmx_scanner_destroy(s);
         return fail(e == cudaErrorMemoryAllocation ? BMX_E_NOMEM : BMX_E_CUDA, "bmx_scanner_create: %s",
@@ -140,6 +143,8 @@ void bmx_scanner_destroy(bmx_scanner *s)
     if (s->h_result) cudaFreeHost(s->h_result);
     if (s->ev_start) cudaEventDestroy(s->ev_start);
     if (s->ev_stop) cudaEventDestroy(s->ev_stop);
+    if (s->ev_k0) cudaEventDestroy(s->ev_k0);
+    if (s->ev_k1) cudaEventDestroy(s->ev_k1);
     delete s;
 }
 
@@ -261,7 +266,9 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
         s->timing_open = true;
     }
     BMX_CUDA(cudaMemsetAsync(s->d_scratch, 0, zero_bytes, st));
+    BMX_CUDA(cudaEventRecord(s->ev_k0, st));
     if (int rc = launch_scan(a, launch, s->positions, st)) return rc;
+    BMX_CUDA(cudaEventRecord(s->ev_k1, st));
     if (s->positions)
         if (int rc = launch_emit(a, st)) return rc;
     BMX_CUDA(cudaEventRecord(s->ev_stop, st));
@@ -289,6 +296,7 @@ int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, vo
         float ms = 0.f;
         BMX_CUDA(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
         s->stats.device_ms = ms;
+        if (s->stats.kernel_launches > 0 && cudaEventElapsedTime(&ms, s->ev_k0, s->ev_k1) == cudaSuccess) s->stats.scan_kernel_ms = ms;
     }
     if (stats) *stats = s->stats;
     return BMX_OK;

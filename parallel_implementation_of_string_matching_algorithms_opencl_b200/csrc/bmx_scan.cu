@@ -626,7 +626,9 @@ __device__ __forceinline__ void expand_segment(const ScanArgs &A, uint32_t seg, 
     }
 }
 
-__device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, unsigned long long carry, uint16_t *stg, int lane)
+// `share`/`member`: the item's segments are dealt round-robin to `share` cooperating warps.
+__device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, unsigned long long carry, uint16_t *stg, int lane,
+                                            uint32_t share, uint32_t member)
 {
     const uint32_t blk = item / kExpandSplit;
     const uint32_t first = (item % kExpandSplit) * kItemSegs;  // first segment of the item inside its block
@@ -657,7 +659,7 @@ __device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, un
         if (lane >= o) incl += t;
     }
     const unsigned long long item_rank = carry + A.block_base[blk] + before;
-    uint32_t vote = __ballot_sync(0xFFFFFFFFu, c != 0);
+    uint32_t vote = __ballot_sync(0xFFFFFFFFu, c != 0 && (uint32_t)lane % share == member);
     while (vote) {
         const int src = __ffs(vote) - 1;
         vote &= vote - 1;
@@ -671,7 +673,11 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
 {
     __shared__ uint16_t s_stage[kExpandWarps][kSegBytes];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t gw = blockIdx.x * kExpandWarps + warp, nw = gridDim.x * kExpandWarps;
+    // A.expand_share warps of a CTA cooperate on one item (1 = a warp per item: best for sparse
+    // texts; 8 = the CTA walks through the item together, which keeps the write streams of a dense
+    // text few and long)
+    const uint32_t share = A.expand_share, groups = kExpandWarps / share;
+    const uint32_t gw = blockIdx.x * groups + warp / share, nw = gridDim.x * groups;
     const uint32_t items = A.num_blocks * kExpandSplit;
     const unsigned long long carry = *A.carry_in;
     for (uint32_t base = 0; base < items; base += nw * 32u) {
@@ -680,7 +686,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
         while (vote) {
             const int src = __ffs(vote) - 1;
             vote &= vote - 1;
-            expand_item(A, __shfl_sync(0xFFFFFFFFu, mine, src), carry, s_stage[warp], lane);
+            expand_item(A, __shfl_sync(0xFFFFFFFFu, mine, src), carry, s_stage[warp], lane, share, warp % share);
         }
     }
 }
@@ -861,6 +867,8 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     a->num_segs = (uint32_t)(tiles * (tile / kSegBytes));
     a->num_blocks = (a->num_segs + kBlockSegs - 1) / kBlockSegs;
     a->owner_offset = variant == BMX_VARIANT_QGRAM ? -3 : 0;
+    a->expand_share = (uint32_t)std::max(1, std::min(8, env_int("BMX_EXPAND_SHARE", 1)));
+    if (kExpandWarps % a->expand_share) a->expand_share = 1;
     out->grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * ctas_per_sm);
 
     const bool full8 = variant == BMX_VARIANT_WINDOW ? a->mulc == 1u : a->mask2 == 0xFFFFFFFFu;
