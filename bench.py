@@ -185,13 +185,16 @@ def run_ours(args):
     stream = torch.cuda.current_stream().cuda_stream
     scanner = bmx.Scanner(local)
     scanner.set_pattern(pat, variant=args.variant, stream=stream)
+    header = torch.zeros(2, dtype=torch.int64, device=dev)
 
     def step():
         scanner.begin(pos, stream=stream)
         scanner.scan(text, lo, stream=stream)
         if world > 1:
-            count, _ = scanner.finish(stream=stream)
-            return bd.combine_hits(count, pos[: min(count, cap)], group=None, device=dev)
+            # exchange step, enqueued behind the scan: count + head of the list travel in one
+            # all-gather, the count all-reduce next to it; one host sync at the end of the step
+            scanner.export_result(header, stream=stream)
+            return bd.combine_hits(None, pos, group=None, device=dev, header=header)
         return None
 
     for _ in range(args.warmup):

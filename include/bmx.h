@@ -166,6 +166,11 @@ int bmx_scanner_begin(bmx_scanner *s, int64_t *d_pos_out, int64_t pos_cap, void 
  * No host synchronisation. */
 int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_base, void *stream);
 
+/* Asynchronously writes {running count, positions actually written = min(count, pos_cap)} as two
+ * int64 into DEVICE memory d_dst on `stream`: lets a multi-GPU caller feed the count exchange
+ * (all-reduce / all-gather) without a host round trip between the scan and the collectives. */
+int bmx_scanner_export_result(bmx_scanner *s, void *d_dst /* int64[2] */, void *stream);
+
 /* Waits for `stream`, returns the running count and (optional) statistics of the scans since
  * bmx_scanner_begin. */
 int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, void *stream);

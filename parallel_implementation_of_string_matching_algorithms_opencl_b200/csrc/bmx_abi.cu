@@ -283,6 +283,14 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     return BMX_OK;
 }
 
+int bmx_scanner_export_result(bmx_scanner *s, void *d_dst, void *stream)
+{
+    if (!s || !d_dst) return fail(BMX_E_BADARG, "bmx_scanner_export_result: NULL argument");
+    BMX_CUDA(cudaSetDevice(s->device));
+    const unsigned long long *src = s->positions ? s->d_ctrl + (s->scan_index & 1u) : s->d_ctrl + 2;
+    return launch_export_result(src, s->pos_cap, d_dst, stream);
+}
+
 int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, void *stream)
 {
     if (!s || !count_out) return fail(BMX_E_BADARG, "bmx_scanner_finish: NULL argument");

@@ -732,6 +732,13 @@ __global__ void synth_fill_kernel(uint8_t *dst, int64_t offset, int64_t len, uin
     }
 }
 
+__global__ void export_result_kernel(const unsigned long long *count, int64_t pos_cap, int64_t *dst)
+{
+    const int64_t c = (int64_t)*count;
+    dst[0] = c;
+    dst[1] = c < pos_cap ? c : pos_cap;
+}
+
 // ans[id] = number of positions p with se[2id] <= p and p + m - 1 <= se[2id+1]
 // (occurrences lying fully inside the inclusive range, kernel1.cl:15,19).
 __global__ void partition_count_kernel(const int64_t *pos, const unsigned long long *count, int64_t pos_cap,
@@ -903,6 +910,14 @@ int launch_emit(const ScanArgs &a, void *stream)
     expand_kernel<<<grid, kExpandThreads, 0, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BMX_E_CUDA, "expand launch: %s", cudaGetErrorString(e));
+    return BMX_OK;
+}
+
+int launch_export_result(const unsigned long long *d_count, int64_t pos_cap, void *d_dst, void *stream)
+{
+    export_result_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_count, pos_cap, static_cast<int64_t *>(d_dst));
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BMX_E_CUDA, "export_result launch: %s", cudaGetErrorString(e));
     return BMX_OK;
 }
 

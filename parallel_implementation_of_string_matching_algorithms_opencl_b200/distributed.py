@@ -36,12 +36,16 @@ def shard_read_range(n_total: int, m: int, lo: int, hi: int) -> tuple[int, int]:
 FAST_GATHER_CAP = 4096  # positions per rank that ride along with the count exchange
 
 
-def combine_hits(count_local: int, positions_local, *, group=None, device=None, dst: int = 0,
-                 fast_cap: int = FAST_GATHER_CAP):
+def combine_hits(count_local, positions_local, *, group=None, device=None, dst: int = 0,
+                 fast_cap: int = FAST_GATHER_CAP, header=None):
     """Exchange step.  Returns (total_count, per_rank_counts, positions_on_dst_or_None).
 
     positions_local: 1-D int64 tensor of this rank's GLOBAL positions (ascending), on `device`
     (it may hold fewer than count_local entries when the caller capped its output).
+    header: optional int64[2] tensor on `device` that already holds (or, stream-ordered, will hold)
+    {count, positions written} -- Scanner.export_result() -- in which case count_local is ignored,
+    positions_local is the whole output buffer and nothing here waits for the scan: the collectives
+    are enqueued behind it and the only host synchronisation is the final read of the counts.
 
     One all-gather carries every rank's [count, list length, first fast_cap positions]; the
     all-reduce of the counts is enqueued next to it and both are awaited with a single host
@@ -54,12 +58,16 @@ def combine_hits(count_local: int, positions_local, *, group=None, device=None, 
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     device = device if device is not None else positions_local.device
-    held_local = 0 if positions_local is None else int(positions_local.numel())
     width = 2 + fast_cap
-
     mine = torch.empty(width, dtype=torch.int64, device=device)
-    mine[:2] = torch.tensor([int(count_local), held_local], dtype=torch.int64)
-    k_local = min(held_local, fast_cap)
+    if header is None:
+        held_local = 0 if positions_local is None else int(positions_local.numel())
+        mine[:2] = torch.tensor([int(count_local), held_local], dtype=torch.int64)
+        k_local = min(held_local, fast_cap)
+    else:
+        held_local = None                      # known only after the header has travelled
+        mine[:2] = header
+        k_local = min(int(positions_local.numel()), fast_cap)   # entries beyond the count are ignored by dst
     if k_local:
         mine[2: 2 + k_local] = positions_local[:k_local]
 
@@ -94,8 +102,8 @@ def combine_hits(count_local: int, positions_local, *, group=None, device=None, 
             off += held_host[r]
         for q in reqs:
             q.wait()
-    elif held_local > fast_cap:
-        dist.send(positions_local[fast_cap:held_local].contiguous(), dst=dst, group=group)
+    elif held_host[rank] > fast_cap:
+        dist.send(positions_local[fast_cap:held_host[rank]].contiguous(), dst=dst, group=group)
     return total_host, counts_host, gathered
 
 

@@ -321,3 +321,35 @@ def test_refmain_demo_prints_the_reference_console_lines(bmx, golden, tmp_path):
     assert all((i == 0) == (p <= 250037) for i, p in found)                   # printed by the owning process
     assert "Serial result (one range, (m-1)-byte halos): 3291 occurrences" in out
     assert "Average time" in out
+
+
+def test_exchange_step_with_device_header(bmx, oracle, dev):
+    """The multi-GPU step as bench.py runs it (scan -> export_result -> collectives), on a
+    one-rank NCCL group: no host sync between the scan and the exchange."""
+    import torch.distributed as dist
+    from parallel_implementation_of_string_matching_algorithms_opencl_b200 import distributed as bd
+
+    text = bmx.synth.fill_host(0, 1 << 20, 61, bmx.synth.ALPHABETS["dna"])
+    pat = text[4242:4250].tobytes()
+    want = oracle.search(text.tobytes(), pat)
+    td = to_dev(text, dev)
+    created = not dist.is_initialized()
+    if created:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29533", rank=0, world_size=1, device_id=dev)
+    try:
+        s = bmx.Scanner(0)
+        stream = torch.cuda.current_stream().cuda_stream
+        s.set_pattern(pat, stream=stream)
+        for cap, fast_cap in [(want.size + 7, 4096), (want.size + 7, 3), (5, 4096)]:
+            pos = torch.empty(cap, dtype=torch.int64, device=dev)
+            header = torch.zeros(2, dtype=torch.int64, device=dev)
+            s.begin(pos, stream=stream)
+            s.scan(td, 1000, stream=stream)
+            s.export_result(header, stream=stream)
+            total, counts, gathered = bd.combine_hits(None, pos, device=dev, header=header, fast_cap=fast_cap)
+            assert total == want.size and counts == [want.size]
+            assert np.array_equal(gathered.cpu().numpy(), (want + 1000)[:cap])
+        s.close()
+    finally:
+        if created:
+            dist.destroy_process_group()
