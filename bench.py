@@ -159,6 +159,8 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU path"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     name = args.workload or ("dna_m32_4GiB" if world == 1 else "ascii95_m64_shard")
@@ -185,20 +187,42 @@ def run_ours(args):
     stream = torch.cuda.current_stream().cuda_stream
     scanner = bmx.Scanner(local)
     scanner.set_pattern(pat, variant=args.variant, stream=stream)
-    header = torch.zeros(2, dtype=torch.int64, device=dev)
+
+    # N > 1: the exchange of step i (count all-reduce + all-gather of the position lists, NCCL) is
+    # enqueued behind scan i and awaited only after the next scans have been queued, so the GPUs
+    # always have a scan to run while the tiny collectives and their host sync complete.
+    depth = 3 if world > 1 else 1
+    ring = [(pos if i == 0 else torch.empty(cap, dtype=torch.int64, device=dev),
+             torch.zeros(2 + bd.FAST_GATHER_CAP, dtype=torch.int64, device=dev)) for i in range(depth)]
+    inflight = []
+    state = {"i": 0, "last": None}
 
     def step():
-        scanner.begin(pos, stream=stream)
+        if world == 1:
+            scanner.begin(pos, stream=stream)
+            scanner.scan(text, lo, stream=stream)
+            return
+        t0 = time.perf_counter()
+        if len(inflight) == depth:
+            state["last"] = inflight.pop(0).finish()
+        t1 = time.perf_counter()
+        p_i, packed_i = ring[state["i"] % depth]
+        state["i"] += 1
+        scanner.begin(p_i, stream=stream)
         scanner.scan(text, lo, stream=stream)
-        if world > 1:
-            # exchange step, enqueued behind the scan: count + head of the list travel in one
-            # all-gather, the count all-reduce next to it; one host sync at the end of the step
-            scanner.export_result(header, stream=stream)
-            return bd.combine_hits(None, pos, group=None, device=dev, header=header)
-        return None
+        scanner.export_result(packed_i, stream=stream)
+        t2 = time.perf_counter()
+        inflight.append(bd.combine_hits_start(None, p_i, group=None, device=dev, packed=packed_i))
+        t3 = time.perf_counter()
+        state["host"] = [a + b for a, b in zip(state.get("host", [0.0, 0.0, 0.0]), (t1 - t0, t2 - t1, t3 - t2))]
+
+    def drain():
+        while inflight:
+            state["last"] = inflight.pop(0).finish()
 
     for _ in range(args.warmup):
         step()
+    drain()
     count, stats = scanner.finish(stream=stream)
     ok = verify_hits(torch, text, lo, pat, pos, count, cap)
 
@@ -209,11 +233,11 @@ def run_ours(args):
     per_step = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     with ClockSampler(local) as clk:
         e0.record()
-        last = None
         for a, b in per_step:
             a.record()
-            last = step()
+            step()
             b.record()
+        drain()
         e1.record()
         if world > 1:
             dist.barrier()
@@ -226,7 +250,9 @@ def run_ours(args):
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-        total_hits = last[0]
+        if state["last"] is not None:
+            total_hits = state["last"][0]
+            ok = ok and state["last"][0] == sum(state["last"][1])
     ms_step = ms_total / args.steps
     value = total_n / (ms_step * 1e-3) / 1e9
 
@@ -282,6 +308,11 @@ def run_ours(args):
         cpu = cpu_baseline(host_sample if host_sample is not None else text.cpu(), pat, threads=1,
                            sample_bytes=args.cpu_sample_bytes)
 
+    if os.environ.get("BENCH_DEBUG") and "host" in state:
+        n_steps = max(state["i"], 1)
+        print(f"[rank {rank}] host ms/step: finish(oldest)={state['host'][0] / n_steps * 1e3:.3f} "
+              f"scan-enqueue={state['host'][1] / n_steps * 1e3:.3f} collectives-enqueue={state['host'][2] / n_steps * 1e3:.3f}",
+              file=sys.stderr, flush=True)
     if rank == 0:
         line = {
             "metric": "text GB/s scanned (device-timed)", "value": value, "unit": "GB/s", "n_gpus": world,

@@ -166,10 +166,12 @@ int bmx_scanner_begin(bmx_scanner *s, int64_t *d_pos_out, int64_t pos_cap, void 
  * No host synchronisation. */
 int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_base, void *stream);
 
-/* Asynchronously writes {running count, positions actually written = min(count, pos_cap)} as two
- * int64 into DEVICE memory d_dst on `stream`: lets a multi-GPU caller feed the count exchange
- * (all-reduce / all-gather) without a host round trip between the scan and the collectives. */
-int bmx_scanner_export_result(bmx_scanner *s, void *d_dst /* int64[2] */, void *stream);
+/* Asynchronously packs the result for a collective into DEVICE memory d_dst on `stream`:
+ * d_dst[0] = running count, d_dst[1] = positions actually written = min(count, pos_cap),
+ * d_dst[2 .. 2+head) = the first `head` entries of the position buffer (entries beyond d_dst[1]
+ * are unspecified).  Lets a multi-GPU caller feed the count exchange (all-reduce / all-gather)
+ * without a host round trip between the scan and the collectives. */
+int bmx_scanner_export_result(bmx_scanner *s, void *d_dst /* int64[2 + head] */, int64_t head, void *stream);
 
 /* Waits for `stream`, returns the running count and (optional) statistics of the scans since
  * bmx_scanner_begin. */

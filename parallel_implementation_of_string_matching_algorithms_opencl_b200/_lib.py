@@ -91,7 +91,7 @@ def load() -> ctypes.CDLL:
     lib.bmx_scanner_set_pattern.argtypes = [c_void_p, c_char_p, c_int32, c_int32, c_void_p]
     lib.bmx_scanner_begin.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.bmx_scanner_scan.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_void_p]
-    lib.bmx_scanner_export_result.argtypes = [c_void_p, c_void_p, c_void_p]
+    lib.bmx_scanner_export_result.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.bmx_scanner_finish.argtypes = [c_void_p, POINTER(c_uint64), POINTER(BmxStats), c_void_p]
     lib.bmx_partition_words.argtypes = [c_void_p, c_int64, c_int32, POINTER(c_int32)]
     lib.bmx_synth_fill_device.argtypes = [c_void_p, c_int64, c_int64, c_uint64, c_char_p, c_int32, c_void_p]

@@ -283,12 +283,12 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     return BMX_OK;
 }
 
-int bmx_scanner_export_result(bmx_scanner *s, void *d_dst, void *stream)
+int bmx_scanner_export_result(bmx_scanner *s, void *d_dst, int64_t head, void *stream)
 {
-    if (!s || !d_dst) return fail(BMX_E_BADARG, "bmx_scanner_export_result: NULL argument");
+    if (!s || !d_dst || head < 0) return fail(BMX_E_BADARG, "bmx_scanner_export_result: bad argument");
     BMX_CUDA(cudaSetDevice(s->device));
     const unsigned long long *src = s->positions ? s->d_ctrl + (s->scan_index & 1u) : s->d_ctrl + 2;
-    return launch_export_result(src, s->pos_cap, d_dst, stream);
+    return launch_export_result(src, s->d_pos_out, s->pos_cap, d_dst, s->positions ? head : 0, stream);
 }
 
 int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, void *stream)

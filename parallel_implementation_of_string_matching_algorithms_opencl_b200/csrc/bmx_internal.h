@@ -89,7 +89,8 @@ int resolve_variant(int requested, int32_t m);
 int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *args, ScanLaunch *out);
 int launch_scan(const ScanArgs &args, const ScanLaunch &launch, bool positions, void *stream);
 int launch_emit(const ScanArgs &args, void *stream);
-int launch_export_result(const unsigned long long *d_count, int64_t pos_cap, void *d_dst, void *stream);   // block-scan + expand (positions mode)
+int launch_export_result(const unsigned long long *d_count, const int64_t *d_pos, int64_t pos_cap, void *d_dst, int64_t head,
+                         void *stream);   // block-scan + expand (positions mode)
 int launch_synth_fill(void *d_text, int64_t offset, int64_t len, uint64_t seed,
                       const unsigned char *alphabet, int32_t sigma, void *stream);
 int launch_partition_count(const int64_t *d_pos, const unsigned long long *d_count, int64_t pos_cap,

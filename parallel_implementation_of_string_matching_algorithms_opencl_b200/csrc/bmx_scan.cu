@@ -732,11 +732,17 @@ __global__ void synth_fill_kernel(uint8_t *dst, int64_t offset, int64_t len, uin
     }
 }
 
-__global__ void export_result_kernel(const unsigned long long *count, int64_t pos_cap, int64_t *dst)
+__global__ void export_result_kernel(const unsigned long long *count, const int64_t *pos, int64_t pos_cap, int64_t *dst,
+                                     int64_t head)
 {
     const int64_t c = (int64_t)*count;
-    dst[0] = c;
-    dst[1] = c < pos_cap ? c : pos_cap;
+    const int64_t held = c < pos_cap ? c : pos_cap;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        dst[0] = c;
+        dst[1] = held;
+    }
+    const int64_t n = head < held ? head : held;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[2 + i] = pos[i];
 }
 
 // ans[id] = number of positions p with se[2id] <= p and p + m - 1 <= se[2id+1]
@@ -876,7 +882,10 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     a->owner_offset = variant == BMX_VARIANT_QGRAM ? -3 : 0;
     a->expand_share = (uint32_t)std::max(1, std::min(8, env_int("BMX_EXPAND_SHARE", 1)));
     if (kExpandWarps % a->expand_share) a->expand_share = 1;
-    out->grid = (int)std::min<int64_t>(tiles, (int64_t)sm_count * ctas_per_sm);
+    // BMX_SPARE_SMS leaves SMs free for concurrently running kernels (the NCCL collectives of a
+    // multi-GPU pipeline cannot start while a persistent grid holds every SM)
+    const int spare = std::max(0, std::min(sm_count - 1, env_int("BMX_SPARE_SMS", 0)));
+    out->grid = (int)std::min<int64_t>(tiles, (int64_t)(sm_count - spare) * ctas_per_sm);
 
     const bool full8 = variant == BMX_VARIANT_WINDOW ? a->mulc == 1u : a->mask2 == 0xFFFFFFFFu;
     const void *k = pick_kernel(variant, full8, tile, positions);
@@ -913,9 +922,12 @@ int launch_emit(const ScanArgs &a, void *stream)
     return BMX_OK;
 }
 
-int launch_export_result(const unsigned long long *d_count, int64_t pos_cap, void *d_dst, void *stream)
+int launch_export_result(const unsigned long long *d_count, const int64_t *d_pos, int64_t pos_cap, void *d_dst, int64_t head,
+                         void *stream)
 {
-    export_result_kernel<<<1, 1, 0, static_cast<cudaStream_t>(stream)>>>(d_count, pos_cap, static_cast<int64_t *>(d_dst));
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((head + 255) / 256, 64));
+    export_result_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(d_count, d_pos, pos_cap,
+                                                                              static_cast<int64_t *>(d_dst), head);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BMX_E_CUDA, "export_result launch: %s", cudaGetErrorString(e));
     return BMX_OK;

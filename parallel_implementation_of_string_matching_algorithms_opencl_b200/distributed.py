@@ -33,78 +33,134 @@ def shard_read_range(n_total: int, m: int, lo: int, hi: int) -> tuple[int, int]:
     return lo, min(n_total, hi + max(m - 1, 0))
 
 
+class PendingExchange:
+    """Collectives of one exchange step, enqueued but not yet awaited (see combine_hits_start)."""
+
+    def __init__(self, works, total, everyone, width, fast_cap, positions_local, group, dst, device):
+        self.works, self.total, self.everyone = works, total, everyone
+        self.width, self.fast_cap, self.positions_local = width, fast_cap, positions_local
+        self.group, self.dst, self.device = group, dst, device
+
+    def finish(self):
+        """Waits for the collectives (the step's single host sync) and assembles the list on dst.
+        Returns (total_count, per_rank_counts, positions_on_dst_or_None).
+
+        On CUDA everything here runs on a side stream that depends only on the collectives, so a
+        caller that has already queued later scans on its compute stream is not held up by them."""
+        import contextlib
+
+        import torch
+        import torch.distributed as dist
+
+        cuda = self.device.type == "cuda"
+        side = _side_stream(self.device) if cuda else None
+        with (torch.cuda.stream(side) if cuda else contextlib.nullcontext()):
+            for w in self.works:
+                w.wait()
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            table = self.everyone.view(world, self.width)
+            header_dev = torch.cat([table[:, :2].reshape(-1), self.total])
+            if cuda:
+                header = torch.empty(header_dev.numel(), dtype=torch.int64, pin_memory=True)
+                header.copy_(header_dev, non_blocking=True)
+                side.synchronize()                                     # the single host sync
+            else:
+                header = header_dev
+            header = header.tolist()
+            counts_host = [int(header[2 * r]) for r in range(world)]
+            held_host = [int(header[2 * r + 1]) for r in range(world)]
+            total_host = int(header[-1])
+            fast_cap, pos = self.fast_cap, self.positions_local
+
+            gathered = None
+            if rank == self.dst:
+                heads = [table[r, 2: 2 + min(held_host[r], fast_cap)] for r in range(world)]
+                if all(h <= fast_cap for h in held_host):
+                    gathered = torch.cat(heads) if heads else torch.empty(0, dtype=torch.int64, device=self.device)
+                else:
+                    gathered = torch.empty(sum(held_host), dtype=torch.int64, device=self.device)
+                    off, reqs = 0, []
+                    for r in range(world):
+                        k = min(held_host[r], fast_cap)
+                        if k:
+                            gathered[off: off + k] = heads[r]
+                        rest = held_host[r] - k
+                        if rest > 0:
+                            if r == self.dst:
+                                gathered[off + k: off + k + rest] = pos[k: k + rest]
+                            else:
+                                reqs.append(dist.irecv(gathered[off + k: off + k + rest], src=r, group=self.group))
+                        off += held_host[r]
+                    for q in reqs:
+                        q.wait()
+            elif held_host[rank] > fast_cap:
+                dist.send(pos[fast_cap:held_host[rank]].contiguous(), dst=self.dst, group=self.group)
+        if cuda:
+            torch.cuda.current_stream(self.device).wait_stream(side)   # later users of `gathered` are ordered after it
+        return total_host, counts_host, gathered
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    import torch
+
+    key = (device.type, device.index)
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _SIDE_STREAMS[key]
+
+
 FAST_GATHER_CAP = 4096  # positions per rank that ride along with the count exchange
 
 
-def combine_hits(count_local, positions_local, *, group=None, device=None, dst: int = 0,
-                 fast_cap: int = FAST_GATHER_CAP, header=None):
-    """Exchange step.  Returns (total_count, per_rank_counts, positions_on_dst_or_None).
+def combine_hits_start(count_local, positions_local, *, group=None, device=None, dst: int = 0,
+                       fast_cap: int = FAST_GATHER_CAP, packed=None) -> PendingExchange:
+    """Enqueues the exchange step and returns without waiting.
 
     positions_local: 1-D int64 tensor of this rank's GLOBAL positions (ascending), on `device`
     (it may hold fewer than count_local entries when the caller capped its output).
-    header: optional int64[2] tensor on `device` that already holds (or, stream-ordered, will hold)
-    {count, positions written} -- Scanner.export_result() -- in which case count_local is ignored,
-    positions_local is the whole output buffer and nothing here waits for the scan: the collectives
-    are enqueued behind it and the only host synchronisation is the final read of the counts.
+    packed: optional int64[2 + fast_cap] tensor on `device` that already holds (or, stream-ordered,
+    will hold) {count, positions written, head of the list} -- Scanner.export_result() -- in which
+    case count_local is ignored, positions_local is the whole output buffer, and nothing here waits
+    for the scan: the collectives are enqueued behind it.
 
     One all-gather carries every rank's [count, list length, first fast_cap positions]; the
-    all-reduce of the counts is enqueued next to it and both are awaited with a single host
-    synchronisation.  Lists longer than fast_cap (dense texts) send their remainder to `dst`
-    point-to-point.  Rank-order concatenation on `dst` is globally ascending, so nothing is sorted.
+    all-reduce of the counts is enqueued next to it.  PendingExchange.finish() awaits both with a
+    single host synchronisation; lists longer than fast_cap (dense texts) send their remainder to
+    `dst` point-to-point.  Rank-order concatenation on `dst` is globally ascending: nothing is sorted.
     """
     import torch
     import torch.distributed as dist
 
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
     device = device if device is not None else positions_local.device
     width = 2 + fast_cap
-    mine = torch.empty(width, dtype=torch.int64, device=device)
-    if header is None:
+    if packed is None:
         held_local = 0 if positions_local is None else int(positions_local.numel())
+        mine = torch.empty(width, dtype=torch.int64, device=device)
         mine[:2] = torch.tensor([int(count_local), held_local], dtype=torch.int64)
         k_local = min(held_local, fast_cap)
+        if k_local:
+            mine[2: 2 + k_local] = positions_local[:k_local]
     else:
-        held_local = None                      # known only after the header has travelled
-        mine[:2] = header
-        k_local = min(int(positions_local.numel()), fast_cap)   # entries beyond the count are ignored by dst
-    if k_local:
-        mine[2: 2 + k_local] = positions_local[:k_local]
+        assert packed.numel() == width and packed.dtype == torch.int64
+        mine = packed
 
     total = mine[:1].clone()
-    work = dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group, async_op=True)   # global hit count
+    works = [dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group, async_op=True)]   # global hit count
     everyone = torch.empty(world * width, dtype=torch.int64, device=device)
     try:
-        dist.all_gather_into_tensor(everyone, mine, group=group)
+        works.append(dist.all_gather_into_tensor(everyone, mine, group=group, async_op=True))
     except (RuntimeError, NotImplementedError):
         _all_gather_list(everyone, mine, group)
-    work.wait()
-    table = everyone.view(world, width)
-    header = torch.cat([table[:, :2].reshape(-1), total]).cpu()        # the single host sync
-    counts_host = [int(header[2 * r]) for r in range(world)]
-    held_host = [int(header[2 * r + 1]) for r in range(world)]
-    total_host = int(header[-1])
+    return PendingExchange(works, total, everyone, width, fast_cap, positions_local, group, dst, device)
 
-    gathered = None
-    if rank == dst:
-        gathered = torch.empty(sum(held_host), dtype=torch.int64, device=device)
-        off, reqs = 0, []
-        for r in range(world):
-            k = min(held_host[r], fast_cap)
-            if k:
-                gathered[off: off + k] = table[r, 2: 2 + k]
-            rest = held_host[r] - k
-            if rest > 0:
-                if r == dst:
-                    gathered[off + k: off + k + rest] = positions_local[k: k + rest]
-                else:
-                    reqs.append(dist.irecv(gathered[off + k: off + k + rest], src=r, group=group))
-            off += held_host[r]
-        for q in reqs:
-            q.wait()
-    elif held_host[rank] > fast_cap:
-        dist.send(positions_local[fast_cap:held_host[rank]].contiguous(), dst=dst, group=group)
-    return total_host, counts_host, gathered
+
+def combine_hits(count_local, positions_local, **kw):
+    """Exchange step, blocking: combine_hits_start(...).finish()."""
+    return combine_hits_start(count_local, positions_local, **kw).finish()
 
 
 def _all_gather_list(out, mine, group):

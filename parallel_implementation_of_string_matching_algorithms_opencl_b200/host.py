@@ -191,9 +191,10 @@ class Scanner:
     def scan(self, text, pos_base=0, stream=0):
         check(self._lib.bmx_scanner_scan(self._h, c_void_p(text.data_ptr()), text.numel(), c_int64(pos_base), c_void_p(stream)))
 
-    def export_result(self, header, stream=0):
-        """Enqueue {count, positions written} into the int64[2] CUDA tensor `header` (no host sync)."""
-        check(self._lib.bmx_scanner_export_result(self._h, c_void_p(header.data_ptr()), c_void_p(stream)))
+    def export_result(self, packed, stream=0):
+        """Enqueue {count, positions written, first len(packed)-2 positions} into the int64 CUDA
+        tensor `packed` (no host sync): the send buffer of the multi-GPU exchange step."""
+        check(self._lib.bmx_scanner_export_result(self._h, c_void_p(packed.data_ptr()), packed.numel() - 2, c_void_p(stream)))
 
     def finish(self, stream=0):
         count = c_uint64(0)

@@ -342,11 +342,12 @@ def test_exchange_step_with_device_header(bmx, oracle, dev):
         s.set_pattern(pat, stream=stream)
         for cap, fast_cap in [(want.size + 7, 4096), (want.size + 7, 3), (5, 4096)]:
             pos = torch.empty(cap, dtype=torch.int64, device=dev)
-            header = torch.zeros(2, dtype=torch.int64, device=dev)
+            packed = torch.zeros(2 + fast_cap, dtype=torch.int64, device=dev)
             s.begin(pos, stream=stream)
             s.scan(td, 1000, stream=stream)
-            s.export_result(header, stream=stream)
-            total, counts, gathered = bd.combine_hits(None, pos, device=dev, header=header, fast_cap=fast_cap)
+            s.export_result(packed, stream=stream)
+            pending = bd.combine_hits_start(None, pos, device=dev, packed=packed, fast_cap=fast_cap)
+            total, counts, gathered = pending.finish()
             assert total == want.size and counts == [want.size]
             assert np.array_equal(gathered.cpu().numpy(), (want + 1000)[:cap])
         s.close()
