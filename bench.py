@@ -35,6 +35,12 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 GIB = 1 << 30
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
 WORKLOADS = {
     # name: (alphabet, bytes per GPU, m, seed, plants per GPU, pattern source)
     "dna_m32_4GiB": dict(alphabet="dna", n=4 * GIB, m=32, seed=43, plants=1000, pattern="from_text"),
@@ -331,7 +337,7 @@ def run_ours(args):
                          "step_frac": step_bytes / (step_gpu_ms * 1e-3) / 1e9 / peak},
             "e2e": e2e, "gpu_launches": int(args.steps) * 2, "clocks": clk.summary(), "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     scanner.close()
     if world > 1:
         dist.barrier()
@@ -415,7 +421,7 @@ def run_reference(args):
     value = n / dt / 1e9
     res["value"] = value
     res["cores"] = threads
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "text GB/s scanned (device-timed)", "value": value, "unit": "GB/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -424,7 +430,7 @@ def run_reference(args):
                    "note": "reference serial BM (its own kernel1.cl + BoyreMoore.cpp tables) run window-parallel on all host threads"},
         "cpu_baseline": res, "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 def main():
@@ -443,6 +449,12 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL's version banner)
+    # are sent to stderr for the duration of the run
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
