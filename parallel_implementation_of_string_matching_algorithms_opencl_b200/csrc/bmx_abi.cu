@@ -239,7 +239,8 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     const size_t off_flag = off_segc + (size_t)a.num_blocks * kBlockSegs * 2;
     const size_t zero_bytes = s->positions ? off_flag + (((size_t)a.num_blocks * kExpandSplit + 15) & ~size_t(15)) : 16;
     const size_t off_bbase = zero_bytes;
-    const size_t off_mask = off_bbase + (size_t)a.num_blocks * 8;
+    const size_t off_dense = off_bbase + (size_t)a.num_blocks * 8;
+    const size_t off_mask = off_dense + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
     const size_t scratch = s->positions ? off_mask + (size_t)a.num_segs * kSegChunks * 2 : 16;
     if (scratch > s->d_scratch_cap) {
         BMX_CUDA(cudaStreamSynchronize(st));
@@ -256,6 +257,7 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     a.seg_count = reinterpret_cast<uint16_t *>(base + off_segc);
     a.item_flag = base + off_flag;
     a.block_base = reinterpret_cast<unsigned long long *>(base + off_bbase);
+    a.dense_list = reinterpret_cast<uint32_t *>(base + off_dense);
     a.mask16 = reinterpret_cast<uint16_t *>(base + off_mask);
     a.carry_in = s->d_ctrl + (s->scan_index & 1u);
     a.carry_out = s->d_ctrl + ((s->scan_index + 1u) & 1u);

@@ -32,6 +32,9 @@ constexpr int kSegBytes = 2048;
 constexpr int kSegChunks = kSegBytes / 16;   // 128
 constexpr int kBlockSegs = 1024;
 constexpr int64_t kBlockBytes = (int64_t)kSegBytes * kBlockSegs;   // 2 MiB
+// A block is "dense" from this many hits on (6 % of its start positions): its items are then expanded in
+// ticket order by whole CTAs, which keeps the write frontier narrow (profiles/micro/write_patterns.cu).
+constexpr uint32_t kDenseBlockHits = 1u << 17;
 constexpr int kExpandSplit = 64;                      // expand work items per block
 constexpr int kItemSegs = kBlockSegs / kExpandSplit;  // 16 segments = 32 KiB of text, one warp each
 
@@ -61,7 +64,8 @@ struct ScanArgs {
     // output
     int64_t *pos_out;
     int64_t pos_cap;
-    uint32_t *tile_counter;                // ticket counter, zeroed before the launch
+    uint32_t *tile_counter;                // [0] tile tickets, [1] CTAs done, [2] dense-item tickets, [3] #dense blocks; zeroed per launch
+    uint32_t *dense_list;                  // indices of the dense blocks, ascending (written by the last CTA)
     uint16_t *mask16;                      // hit mask per chunk (written only where a segment has hits)
     uint16_t *seg_count;                   // hits per segment, zeroed before the launch
     uint32_t *block_sum;                   // hits per block, zeroed before the launch

@@ -518,6 +518,24 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         bar_sync_consumers();
     }
     if (tid == 0) *A.carry_out = *A.carry_in + ctl->scan_running;
+
+    // list of the dense blocks, ascending (expand_kernel walks them in ticket order)
+    if (tid == 0) ctl->scan_running = 0;
+    bar_sync_consumers();
+    for (uint32_t base = 0; base < A.num_blocks; base += kConsumerThreads) {
+        const uint32_t b = base + tid;
+        const bool dense = b < A.num_blocks && __ldcg(&A.block_sum[b]) >= kDenseBlockHits;
+        const uint32_t votes = __ballot_sync(0xFFFFFFFFu, dense);
+        if (lane == 0) ctl->scan_warp[warp] = __popc(votes);
+        bar_sync_consumers();
+        unsigned long long before = ctl->scan_running;
+        for (int w = 0; w < warp; ++w) before += ctl->scan_warp[w];
+        if (dense) A.dense_list[before + __popc(votes & ((1u << lane) - 1u))] = b;
+        bar_sync_consumers();
+        if (tid == kConsumerThreads - 1) ctl->scan_running = before + __popc(votes);
+        bar_sync_consumers();
+    }
+    if (tid == 0) A.tile_counter[3] = (uint32_t)ctl->scan_running;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -672,22 +690,40 @@ __device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, un
 __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_constant__ ScanArgs A)
 {
     __shared__ uint16_t s_stage[kExpandWarps][kSegBytes];
+    __shared__ uint32_t s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // A.expand_share warps of a CTA cooperate on one item (1 = a warp per item: best for sparse
-    // texts; 8 = the CTA walks through the item together, which keeps the write streams of a dense
-    // text few and long)
-    const uint32_t share = A.expand_share, groups = kExpandWarps / share;
-    const uint32_t gw = blockIdx.x * groups + warp / share, nw = gridDim.x * groups;
-    const uint32_t items = A.num_blocks * kExpandSplit;
     const unsigned long long carry = *A.carry_in;
-    for (uint32_t base = 0; base < items; base += nw * 32u) {
-        const uint32_t mine = base + (uint32_t)lane * nw + gw;
-        uint32_t vote = __ballot_sync(0xFFFFFFFFu, mine < items && A.item_flag[mine] != 0);
-        while (vote) {
-            const int src = __ffs(vote) - 1;
-            vote &= vote - 1;
-            expand_item(A, __shfl_sync(0xFFFFFFFFu, mine, src), carry, s_stage[warp], lane, share, warp % share);
+
+    // ---- phase 1: items of sparse blocks, one warp per item, found by one round of flag probes
+    {
+        const uint32_t share = A.expand_share, groups = kExpandWarps / share;
+        const uint32_t gw = blockIdx.x * groups + warp / share, nw = gridDim.x * groups;
+        const uint32_t items = A.num_blocks * kExpandSplit;
+        for (uint32_t base = 0; base < items; base += nw * 32u) {
+            const uint32_t mine = base + (uint32_t)lane * nw + gw;
+            uint32_t vote = __ballot_sync(0xFFFFFFFFu, mine < items && A.item_flag[mine] != 0 &&
+                                                           A.block_sum[mine / kExpandSplit] < kDenseBlockHits);
+            while (vote) {
+                const int src = __ffs(vote) - 1;
+                vote &= vote - 1;
+                expand_item(A, __shfl_sync(0xFFFFFFFFu, mine, src), carry, s_stage[warp], lane, share, warp % share);
+            }
         }
+    }
+
+    // ---- phase 2: items of dense blocks in ticket order, a whole CTA per item (each warp two of its
+    // segments).  In-order tickets keep the write frontier of the grid narrow and moving linearly, which
+    // is what reaches the HBM write peak (7.2-7.6 TB/s vs 5.6-6.3 TB/s for static striding).
+    const uint32_t dense_items = A.tile_counter[3] * kExpandSplit;
+    if (dense_items == 0) return;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_ticket = atomicAdd(A.tile_counter + 2, 1u);
+        __syncthreads();
+        const uint32_t t = s_ticket;
+        if (t >= dense_items) break;
+        const uint32_t item = A.dense_list[t / kExpandSplit] * kExpandSplit + t % kExpandSplit;
+        if (A.item_flag[item] != 0) expand_item(A, item, carry, s_stage[warp], lane, kExpandWarps, (uint32_t)warp);
     }
 }
 
