@@ -103,7 +103,7 @@ struct SmemCtl {
     int32_t slot_tile[kMaxStages]; // tile index staged in each slot, -1 = no more tiles
     uint32_t is_last;              // this CTA finished last: it scans the block sums
     unsigned long long scan_warp[kConsumerWarps];
-    unsigned long long scan_running;
+    uint32_t scan_dense[kConsumerWarps];
     int32_t bad[256];              // bad-symbol table   (BoyreMoore.cpp:153-162)
     uint32_t sa_mask[256];         // Shift-And occurrence masks
     int32_t good[kPatSmemMax];     // good-suffix table  (BoyreMoore.cpp:165-190)
@@ -497,45 +497,53 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     bar_sync_consumers();
     if (!ctl->is_last) return;
     __threadfence();
-    if (tid == 0) ctl->scan_running = 0;
-    bar_sync_consumers();
-    for (uint32_t base = 0; base < A.num_blocks; base += kConsumerThreads) {
-        const uint32_t b = base + tid;
-        const unsigned long long v = b < A.num_blocks ? __ldcg(&A.block_sum[b]) : 0ull;
-        unsigned long long incl = v;
+    // One pass: thread t owns a contiguous run of blocks, sums it (hits and dense blocks), the CTA scans
+    // the 256 partial sums, then every thread writes the bases and the dense list of its run.
+    const uint32_t per = (A.num_blocks + kConsumerThreads - 1) / kConsumerThreads;
+    const uint32_t b0 = min((uint32_t)tid * per, A.num_blocks), b1 = min(b0 + per, A.num_blocks);
+    unsigned long long hits = 0;
+    uint32_t ndense = 0;
+    for (uint32_t b = b0; b < b1; ++b) {
+        const uint32_t v = __ldcg(&A.block_sum[b]);
+        hits += v;
+        ndense += v >= kDenseBlockHits ? 1u : 0u;
+    }
+    unsigned long long hits_incl = hits;
+    uint32_t dense_incl = ndense;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long t = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += t;
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long th = __shfl_up_sync(0xFFFFFFFFu, hits_incl, o);
+        const uint32_t td = __shfl_up_sync(0xFFFFFFFFu, dense_incl, o);
+        if (lane >= o) {
+            hits_incl += th;
+            dense_incl += td;
         }
-        if (lane == 31) ctl->scan_warp[warp] = incl;
-        bar_sync_consumers();
-        unsigned long long before = ctl->scan_running;
-        for (int w = 0; w < warp; ++w) before += ctl->scan_warp[w];
-        if (b < A.num_blocks) A.block_base[b] = before + (incl - v);
-        bar_sync_consumers();
-        if (tid == kConsumerThreads - 1) ctl->scan_running = before + incl;
-        bar_sync_consumers();
     }
-    if (tid == 0) *A.carry_out = *A.carry_in + ctl->scan_running;
-
-    // list of the dense blocks, ascending (expand_kernel walks them in ticket order)
-    if (tid == 0) ctl->scan_running = 0;
+    if (lane == 31) {
+        ctl->scan_warp[warp] = hits_incl;
+        ctl->scan_dense[warp] = dense_incl;
+    }
     bar_sync_consumers();
-    for (uint32_t base = 0; base < A.num_blocks; base += kConsumerThreads) {
-        const uint32_t b = base + tid;
-        const bool dense = b < A.num_blocks && __ldcg(&A.block_sum[b]) >= kDenseBlockHits;
-        const uint32_t votes = __ballot_sync(0xFFFFFFFFu, dense);
-        if (lane == 0) ctl->scan_warp[warp] = __popc(votes);
-        bar_sync_consumers();
-        unsigned long long before = ctl->scan_running;
-        for (int w = 0; w < warp; ++w) before += ctl->scan_warp[w];
-        if (dense) A.dense_list[before + __popc(votes & ((1u << lane) - 1u))] = b;
-        bar_sync_consumers();
-        if (tid == kConsumerThreads - 1) ctl->scan_running = before + __popc(votes);
-        bar_sync_consumers();
+    unsigned long long hits_before = hits_incl - hits, total_hits = 0;
+    uint32_t dense_before = dense_incl - ndense, total_dense = 0;
+    for (int w = 0; w < kConsumerWarps; ++w) {
+        if (w < warp) {
+            hits_before += ctl->scan_warp[w];
+            dense_before += ctl->scan_dense[w];
+        }
+        total_hits += ctl->scan_warp[w];
+        total_dense += ctl->scan_dense[w];
     }
-    if (tid == 0) A.tile_counter[3] = (uint32_t)ctl->scan_running;
+    for (uint32_t b = b0; b < b1; ++b) {
+        const uint32_t v = __ldcg(&A.block_sum[b]);
+        A.block_base[b] = hits_before;
+        hits_before += v;
+        if (v >= kDenseBlockHits) A.dense_list[dense_before++] = b;  // ascending: expand_kernel walks it in ticket order
+    }
+    if (tid == 0) {
+        *A.carry_out = *A.carry_in + total_hits;
+        A.tile_counter[3] = total_dense;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
