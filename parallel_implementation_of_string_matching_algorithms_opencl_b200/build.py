@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo",
-    "-Xcompiler", "-fPIC,-Wall",
+    "-Xcompiler", "-fPIC,-Wall,-pthread",
 ]
 
 

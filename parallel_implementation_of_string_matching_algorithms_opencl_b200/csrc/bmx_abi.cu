@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "bmx_internal.h"
@@ -367,6 +368,24 @@ int ensure_streams(ThreadCtx &c, int device, size_t nevents)
     return BMX_OK;
 }
 
+// memcpy split over a few host threads: one core moves ~10 GB/s, a PCIe Gen5 x16 link takes ~55 GB/s
+void parallel_copy(void *dst, const void *src, size_t bytes, int threads)
+{
+    if (threads <= 1 || bytes < (size_t(8) << 20)) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    const size_t slice = ((bytes / (size_t)threads) + 4095) & ~size_t(4095);
+    std::vector<std::thread> helpers;
+    for (int t = 1; t < threads; ++t) {
+        const size_t lo = std::min(bytes, slice * (size_t)t), hi = std::min(bytes, lo + slice);
+        if (hi > lo)
+            helpers.emplace_back([=] { memcpy(static_cast<char *>(dst) + lo, static_cast<const char *>(src) + lo, hi - lo); });
+    }
+    memcpy(dst, src, std::min(bytes, slice));
+    for (auto &h : helpers) h.join();
+}
+
 bool is_pinned_host(const void *p)
 {
     cudaPointerAttributes attr;
@@ -465,6 +484,9 @@ int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int3
     }
 
     const bool pinned = is_pinned_host(text);
+    int staging_threads = 8;  // host threads that fill a pinned bounce buffer from pageable memory (profiles/e2e_host_memory.py)
+    if (const char *e = getenv("BMX_STAGING_THREADS")) staging_threads = std::max(1, std::min(32, atoi(e)));
+    staging_threads = (int)std::max(1u, std::min<unsigned>((unsigned)staging_threads, std::thread::hardware_concurrency()));
     if (!pinned && c->bounce_bytes < (size_t)std::min(chunk, n)) {
         for (int b = 0; b < kBounce; ++b) {
             if (c->bounce[b]) cudaFreeHost(c->bounce[b]);
@@ -484,7 +506,7 @@ int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int3
             const int b = (int)(k % kBounce);
             // the bounce buffer is free once the copy that used it kBounce chunks ago has finished
             if (k >= kBounce) BMX_TRY(cudaEventSynchronize(c->events[(size_t)nchunks + (size_t)b]));
-            memcpy(c->bounce[b], src, (size_t)len);
+            parallel_copy(c->bounce[b], src, (size_t)len, staging_threads);
             src = reinterpret_cast<const char *>(c->bounce[b]);
             BMX_TRY(cudaMemcpyAsync(d_text + off, src, (size_t)len, cudaMemcpyHostToDevice, c->copy_stream));
             BMX_TRY(cudaEventRecord(c->events[(size_t)nchunks + (size_t)b], c->copy_stream));
