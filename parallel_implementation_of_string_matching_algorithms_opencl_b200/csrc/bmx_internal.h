@@ -73,7 +73,6 @@ struct ScanArgs {
     unsigned long long *block_base;        // exclusive prefix of block_sum (block-scan kernel)
     uint32_t num_segs;
     uint32_t num_blocks;
-    uint32_t expand_share;                 // warps of a CTA cooperating on one expand item (1, 2, 4 or 8)
     int32_t owner_offset;                  // start position of mask bit 0 relative to its chunk (-3 for QGRAM)
     const unsigned long long *carry_in;    // hits reported by earlier chained scans
     unsigned long long *carry_out;         // carry_in + hits of this scan (block-scan kernel)

@@ -704,8 +704,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
 
     // ---- phase 1: items of sparse blocks, one warp per item, found by one round of flag probes
     {
-        const uint32_t share = A.expand_share, groups = kExpandWarps / share;
-        const uint32_t gw = blockIdx.x * groups + warp / share, nw = gridDim.x * groups;
+        const uint32_t gw = blockIdx.x * kExpandWarps + warp, nw = gridDim.x * kExpandWarps;
         const uint32_t items = A.num_blocks * kExpandSplit;
         for (uint32_t base = 0; base < items; base += nw * 32u) {
             const uint32_t mine = base + (uint32_t)lane * nw + gw;
@@ -714,7 +713,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
             while (vote) {
                 const int src = __ffs(vote) - 1;
                 vote &= vote - 1;
-                expand_item(A, __shfl_sync(0xFFFFFFFFu, mine, src), carry, s_stage[warp], lane, share, warp % share);
+                expand_item(A, __shfl_sync(0xFFFFFFFFu, mine, src), carry, s_stage[warp], lane, 1u, 0u);
             }
         }
     }
@@ -924,8 +923,6 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     a->num_segs = (uint32_t)(tiles * (tile / kSegBytes));
     a->num_blocks = (a->num_segs + kBlockSegs - 1) / kBlockSegs;
     a->owner_offset = variant == BMX_VARIANT_QGRAM ? -3 : 0;
-    a->expand_share = (uint32_t)std::max(1, std::min(8, env_int("BMX_EXPAND_SHARE", 1)));
-    if (kExpandWarps % a->expand_share) a->expand_share = 1;
     // BMX_SPARE_SMS leaves SMs free for concurrently running kernels (the NCCL collectives of a
     // multi-GPU pipeline cannot start while a persistent grid holds every SM)
     const int spare = std::max(0, std::min(sm_count - 1, env_int("BMX_SPARE_SMS", 0)));

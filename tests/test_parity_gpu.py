@@ -354,3 +354,28 @@ def test_exchange_step_with_device_header(bmx, oracle, dev):
     finally:
         if created:
             dist.destroy_process_group()
+
+
+def test_mid_density_and_mixed_blocks(bmx, oracle, dev):
+    """Texts whose 2 MiB blocks are dense with PARTIAL hit masks (ticket-ordered CTA expand, staged
+    stores), sparse, or a mix of both; capacity truncation inside a dense block."""
+    rng = np.random.default_rng(77)
+    n = (6 << 20) + 4321
+    binary = rng.integers(0, 2, size=n, dtype=np.uint8) + 97           # 'a'/'b': 25 % of starts match 'ab'
+    mixed = rng.integers(0, 256, size=n, dtype=np.uint8)
+    mixed[: (2 << 20) + 999] = binary[: (2 << 20) + 999]               # dense block, then sparse, then dense again
+    mixed[-(1 << 20):] = ord("a")
+    periodic = np.frombuffer((b"abc" * (n // 3 + 1))[:n], dtype=np.uint8).copy()
+    for text, pats in [(binary, [b"ab", b"aab", b"abab", b"abbabaab"]), (mixed, [b"ab", b"aa", b"aaaaaaaaa"]),
+                       (periodic, [b"abc", b"bcab", b"cabcabcabcab"])]:
+        td = to_dev(text, dev, misalign=3)
+        for pat in pats:
+            want = oracle.search_np(text, pat, threads=-1)
+            assert want.size > 1000
+            count, pos, _ = bmx.search_device(td, pat, max_positions=n)
+            assert count == want.size and np.array_equal(pos.cpu().numpy(), want), pat
+            cap = want.size // 2 + 1
+            count, pos, _ = bmx.search_device(td, pat, max_positions=cap)
+            assert count == want.size and np.array_equal(pos.cpu().numpy(), want[:cap]), (pat, "truncated")
+            count, _, _ = bmx.search_device(td, pat)
+            assert count == want.size
