@@ -240,7 +240,7 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     const size_t off_flag = off_segc + (size_t)a.num_blocks * kBlockSegs * 2;
     const size_t zero_bytes = s->positions ? off_flag + (((size_t)a.num_blocks * kExpandSplit + 15) & ~size_t(15)) : 16;
     const size_t off_bbase = zero_bytes;
-    const size_t off_dense = off_bbase + (size_t)a.num_blocks * 8;
+    const size_t off_dense = off_bbase + (((size_t)a.num_blocks * 8 + 15) & ~size_t(15));  // mask16 is read with 16-byte loads
     const size_t off_mask = off_dense + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
     const size_t scratch = s->positions ? off_mask + (size_t)a.num_segs * kSegChunks * 2 : 16;
     if (scratch > s->d_scratch_cap) {

@@ -286,6 +286,11 @@ __device__ __forceinline__ void publish_segment(const ScanArgs &A, uint32_t seg,
     }
 }
 
+// A warp switches to dense_tile() for its next tile when, on average, this many of its lanes held
+// candidates in each segment of the current tile: then the any-pass + vote + recompute of the sparse
+// path costs more than building every lane's masks right away.
+constexpr uint32_t kDenseLanes = 6;
+
 struct VerifyCtx {
     const uint8_t *vbase, *pat;
     const int32_t *bad, *good;
@@ -303,28 +308,30 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
     constexpr int WARP_BYTES = TILE / kConsumerWarps;
     constexpr int OFFS = VARIANT == kQgram ? -3 : 0;
     unsigned long long found = 0;
-    bool still_dense = true;
+    uint32_t cand_lanes = 0;
     for (int sg = 0; sg < WARP_BYTES / kSegBytes; ++sg) {
         const uint32_t seg_off = warp * WARP_BYTES + sg * kSegBytes;
         const int64_t seg_p0 = tile_v0 + seg_off + lane * 16 + OFFS;
         uint4 w[4];
         uint32_t w4[4], hm[4], seg_hits = 0;
         load_segment(st + seg_off, lane, w, w4);
+        uint32_t any_cand = 0;
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
             const int64_t p0 = seg_p0 + sl * 512;
             uint32_t cand = filter_mask<VARIANT, FLAG>(w[sl], w4[sl], A);
             if (!vc.all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
+            any_cand |= cand;
             hm[sl] = 0;
             if (cand) hm[sl] = vc.exact_filter ? cand : verify_candidates(cand, vc.vbase, p0, A.m, vc.pat, vc.bad, vc.good);
             seg_hits += __popc(hm[sl]);
         }
+        cand_lanes += __popc(__ballot_sync(0xFFFFFFFFu, any_cand != 0));
         const uint32_t hit_lanes = __ballot_sync(0xFFFFFFFFu, seg_hits != 0);
-        still_dense = __popc(hit_lanes) >= 24;
         found += seg_hits;
         if (POSITIONS && hit_lanes) publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
     }
-    return found | (still_dense ? (1ull << 63) : 0ull);
+    return found | (cand_lanes >= kDenseLanes * (WARP_BYTES / kSegBytes) ? (1ull << 63) : 0ull);
 }
 
 template <int VARIANT, bool FULL8, int TILE, bool POSITIONS>
@@ -431,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
             dense_mode = (r >> 63) != 0;
             if (!POSITIONS) my_count += r & ~(1ull << 63);
         } else {
+            uint32_t cand_lanes = 0;
 #pragma unroll
             for (int sg = 0; sg < SEGS; ++sg) {
                 uint32_t hm[4] = {0u, 0u, 0u, 0u};
@@ -468,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                             }
                         }
                         has_hits = __any_sync(0xFFFFFFFFu, seg_hits != 0);
-                        dense_mode = __popc(vote) >= 24;  // takes effect with the next tile
+                        cand_lanes += __popc(vote);
                     }
                 }
                 if (has_hits) {
@@ -476,6 +484,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                     else publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
                 }
             }
+            dense_mode = cand_lanes >= kDenseLanes * SEGS;  // takes effect with the next tile
         }
         // every lane is done reading the stage: hand it back to the producer
         __syncwarp();
@@ -552,6 +561,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
 constexpr int kExpandThreads = 256;
 constexpr int kExpandWarps = kExpandThreads / 32;
 constexpr uint32_t kStageThreshold = 96;  // segments with more hits go through shared memory
+constexpr uint32_t kSoloMaxHits = 64;     // segments with at most this many hits are expanded by a single lane
 
 // Warp-cooperative store of out[0..limit) = value(r) with 16-byte vector stores: lane l writes the
 // element pairs (2l, 2l+1) + 64j of the 16-byte aligned middle part, one lane each the ragged ends.
@@ -580,7 +590,7 @@ __device__ __forceinline__ void store_run(int64_t *out, uint32_t limit, int lane
 // Lane l of warp g probes the flag of item (32*round + l) * #warps + g, so one round of loads finds
 // all work of a sparse text (every flagged item gets its own warp), and a dense text spreads evenly.
 __device__ __forceinline__ void expand_segment(const ScanArgs &A, uint32_t seg, uint32_t cnt, unsigned long long seg_rank,
-                                               uint16_t *stg, int lane)
+                                               const uint32_t (&hm)[4], uint16_t *stg, int lane)
 {
     const int64_t cap = A.pos_cap;
     if ((int64_t)seg_rank >= cap) return;  // truncated output keeps the smallest positions
@@ -594,10 +604,6 @@ __device__ __forceinline__ void expand_segment(const ScanArgs &A, uint32_t seg, 
         store_run(out, limit, lane, [&](uint32_t r) { return seg_pos + (int64_t)r; });
         return;
     }
-    const uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
-    uint32_t hm[4];
-#pragma unroll
-    for (int sl = 0; sl < 4; ++sl) hm[sl] = mk[sl * 32];
     // one warp scan for all four slabs: two words of two 16-bit counters each
     uint32_t p01 = __popc(hm[0]) | (__popc(hm[1]) << 16);
     uint32_t p23 = __popc(hm[2]) | (__popc(hm[3]) << 16);
@@ -685,13 +691,68 @@ __device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, un
         if (lane >= o) incl += t;
     }
     const unsigned long long item_rank = carry + A.block_base[blk] + before;
-    uint32_t vote = __ballot_sync(0xFFFFFFFFu, c != 0 && (uint32_t)lane % share == member);
+    // Segments with few hits (the common case of natural-language text: a dozen hits per 2 KiB) are
+    // expanded by ONE lane each -- lane l walks the 128 masks of segment l, 16 lanes in parallel --
+    // which costs a tenth of the warp-cooperative path's instructions.
+    const bool solo = share == 1 && c != 0 && c <= kSoloMaxHits;
+    if (solo) {
+        const uint32_t seg = seg0 + lane;
+        const unsigned long long seg_rank = item_rank + (incl - c);
+        const int64_t room = A.pos_cap - (int64_t)seg_rank;
+        if (room > 0) {
+            const int64_t seg_pos = (int64_t)seg * kSegBytes + A.owner_offset + A.pos_bias;
+            int64_t *out = A.pos_out + seg_rank;
+            const uint4 *mp = reinterpret_cast<const uint4 *>(A.mask16 + (size_t)seg * kSegChunks);
+            uint32_t written = 0;
+            for (int q0 = 0; q0 < kSegChunks / 8; q0 += 4) {
+                uint4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = mp[q0 + u];  // 4 x 8 masks in flight
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint32_t ws[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint32_t w = ws[j];  // masks of chunks 8q+2j (low half) and 8q+2j+1 (high half)
+                        const uint32_t local0 = ((q0 + u) * 8 + j * 2) * 16;
+                        while (w) {
+                            const uint32_t b = __ffs(w) - 1;
+                            w &= w - 1;
+                            if ((int64_t)written < room) out[written] = seg_pos + local0 + b;
+                            ++written;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    uint32_t vote = __ballot_sync(0xFFFFFFFFu, c != 0 && !solo && (uint32_t)lane % share == member);
     while (vote) {
-        const int src = __ffs(vote) - 1;
-        vote &= vote - 1;
-        const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, c, src);
-        const uint32_t off = __shfl_sync(0xFFFFFFFFu, incl - c, src);
-        expand_segment(A, seg0 + src, cnt, item_rank + off, stg, lane);
+        // up to 4 segments per round: all their mask loads are issued before any is expanded
+        int src[4];
+        uint32_t hm[4][4];
+        int k = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            src[j] = 0;
+            if (vote) {
+                src[j] = __ffs(vote) - 1;
+                vote &= vote - 1;
+                k = j + 1;
+                const uint16_t *mk = A.mask16 + (size_t)(seg0 + src[j]) * kSegChunks + lane;
+                const bool full = __shfl_sync(0xFFFFFFFFu, c, src[j]) == kSegBytes;  // full segments have no masks
+#pragma unroll
+                for (int sl = 0; sl < 4; ++sl) hm[j][sl] = full ? 0xFFFFu : mk[sl * 32];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < k) {
+                const uint32_t cnt = __shfl_sync(0xFFFFFFFFu, c, src[j]);
+                const uint32_t off = __shfl_sync(0xFFFFFFFFu, incl - c, src[j]);
+                expand_segment(A, seg0 + src[j], cnt, item_rank + off, hm[j], stg, lane);
+            }
+        }
     }
 }
 
