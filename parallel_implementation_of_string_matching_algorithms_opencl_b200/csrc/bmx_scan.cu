@@ -267,13 +267,13 @@ __device__ __forceinline__ void load_segment(const uint8_t *sp, int lane, uint4 
     }
 }
 
-// A warp whose segment has hits publishes its masks and its count (no waiting on anyone).
-__device__ __forceinline__ void publish_segment(const ScanArgs &A, uint32_t seg, const uint32_t (&hm)[4],
-                                                uint32_t seg_hits, int lane)
+// A warp whose segment has hits publishes its masks and its count (no waiting on anyone) and returns
+// the segment's hit count; the caller adds a warp's counts of one tile to the block sum in one atomic
+// (the per-segment atomics of an every-segment-hits text queued up on a handful of L2 addresses).
+__device__ __forceinline__ uint32_t publish_segment(const ScanArgs &A, uint32_t seg, const uint32_t (&hm)[4],
+                                                    uint32_t seg_hits, int lane)
 {
-    uint32_t total = seg_hits;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+    const uint32_t total = __reduce_add_sync(0xFFFFFFFFu, seg_hits);  // REDUX.SUM
     if (total != kSegBytes) {  // a full segment (every start matches) needs no masks
         uint16_t *mk = A.mask16 + (size_t)seg * kSegChunks + lane;
 #pragma unroll
@@ -282,8 +282,8 @@ __device__ __forceinline__ void publish_segment(const ScanArgs &A, uint32_t seg,
     if (lane == 0) {
         A.seg_count[seg] = (uint16_t)total;
         A.item_flag[seg / kItemSegs] = 1;  // benign race: every writer stores 1
-        atomicAdd(&A.block_sum[seg / kBlockSegs], total);
     }
+    return total;
 }
 
 // A warp switches to dense_tile() for its next tile when, on average, this many of its lanes held
@@ -308,7 +308,7 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
     constexpr int WARP_BYTES = TILE / kConsumerWarps;
     constexpr int OFFS = VARIANT == kQgram ? -3 : 0;
     unsigned long long found = 0;
-    uint32_t cand_lanes = 0;
+    uint32_t cand_lanes = 0, tile_total = 0;
     for (int sg = 0; sg < WARP_BYTES / kSegBytes; ++sg) {
         const uint32_t seg_off = warp * WARP_BYTES + sg * kSegBytes;
         const int64_t seg_p0 = tile_v0 + seg_off + lane * 16 + OFFS;
@@ -329,8 +329,10 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
         cand_lanes += __popc(__ballot_sync(0xFFFFFFFFu, any_cand != 0));
         const uint32_t hit_lanes = __ballot_sync(0xFFFFFFFFu, seg_hits != 0);
         found += seg_hits;
-        if (POSITIONS && hit_lanes) publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
+        if (POSITIONS && hit_lanes) tile_total += publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
     }
+    if (POSITIONS && tile_total && lane == 0)
+        atomicAdd(&A.block_sum[(uint32_t)((tile_v0 + warp * WARP_BYTES) / kBlockBytes)], tile_total);
     return found | (cand_lanes >= kDenseLanes * (WARP_BYTES / kSegBytes) ? (1ull << 63) : 0ull);
 }
 
@@ -438,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
             dense_mode = (r >> 63) != 0;
             if (!POSITIONS) my_count += r & ~(1ull << 63);
         } else {
-            uint32_t cand_lanes = 0;
+            uint32_t cand_lanes = 0, tile_total = 0;
 #pragma unroll
             for (int sg = 0; sg < SEGS; ++sg) {
                 uint32_t hm[4] = {0u, 0u, 0u, 0u};
@@ -481,9 +483,11 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                 }
                 if (has_hits) {
                     if (!POSITIONS) my_count += seg_hits;
-                    else publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
+                    else tile_total += publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
                 }
             }
+            if (POSITIONS && tile_total && lane == 0)  // a warp's 4 KiB of a tile lie inside one 2 MiB block
+                atomicAdd(&A.block_sum[(uint32_t)((tile_v0 + warp * WARP_BYTES) / kBlockBytes)], tile_total);
             dense_mode = cand_lanes >= kDenseLanes * SEGS;  // takes effect with the next tile
         }
         // every lane is done reading the stage: hand it back to the producer
@@ -704,12 +708,12 @@ __device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, un
             int64_t *out = A.pos_out + seg_rank;
             const uint4 *mp = reinterpret_cast<const uint4 *>(A.mask16 + (size_t)seg * kSegChunks);
             uint32_t written = 0;
-            for (int q0 = 0; q0 < kSegChunks / 8; q0 += 4) {
-                uint4 v[4];
+            for (int q0 = 0; q0 < kSegChunks / 8; q0 += 8) {
+                uint4 v[8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) v[u] = mp[q0 + u];  // 4 x 8 masks in flight
+                for (int u = 0; u < 8; ++u) v[u] = mp[q0 + u];  // 8 x 8 masks in flight
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < 8; ++u) {
                     const uint32_t ws[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {

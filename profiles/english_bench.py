@@ -44,7 +44,7 @@ for pat in (b"is", b"the", b" ", b"position", b"HACKHACK", b"occurrences startin
         torch.cuda.synchronize()
         cnt, st = sc.finish(stream=stream)
         ms = e0.elapsed_time(e1) / 10
-        res.append(f"{mode}: {n / ms / 1e6:7.1f} GB/s ({ms * 1e3:7.1f} us)")
+        res.append(f"{mode}: {n / ms / 1e6:7.1f} GB/s ({ms * 1e3:7.1f} us, scan kernel {st['scan_kernel_ms'] * 1e3:6.1f} us)")
     # parity on the first 64 MiB against the oracle
     w = 64 << 20
     sc.begin(pos, stream=stream)

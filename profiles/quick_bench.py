@@ -47,7 +47,7 @@ for name in names:
         ms = e0.elapsed_time(e1) / 20
         gbs = n / (ms * 1e-3) / 1e9
         traffic = (n + (8 * cnt if mode == "positions" else 0)) / (ms * 1e-3) / 1e9
-        out.append(f"{mode}: {gbs:7.1f} GB/s scanned ({traffic:7.1f} GB/s algorithmic, {ms * 1e3:8.1f} us)")
+        out.append(f"{mode}: {gbs:7.1f} GB/s scanned ({traffic:7.1f} GB/s algorithmic, {ms * 1e3:8.1f} us, scan kernel {st['scan_kernel_ms'] * 1e3:7.1f} us)")
     ok = bench.verify_hits(torch, text, 0, pat, pos, cnt, cap)
     print(f"{name:22s} {st['variant']:8s} hits={cnt:<11d} ok={ok}  " + "  |  ".join(out), flush=True)
     del text, pos
