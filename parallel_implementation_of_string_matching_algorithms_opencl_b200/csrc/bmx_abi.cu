@@ -167,7 +167,7 @@ int bmx_scanner_set_pattern(bmx_scanner *s, const char *pat, int32_t m, int32_t 
     // Host image of the device block: tables once per pattern (BoyreMoore.cpp:153-190).
     const size_t good_off = 256 * sizeof(int32_t);
     const size_t pat_off = good_off + (size_t)m * sizeof(int32_t);
-    const size_t bytes = (pat_off + (size_t)m + 15) & ~size_t(15);
+    const size_t bytes = ((pat_off + (size_t)m + 15) & ~size_t(15)) + 16;  // verification reads aligned word pairs
     std::vector<unsigned char> image(bytes, 0);
     build_bad_table(p, m, reinterpret_cast<int32_t *>(image.data()));
     build_good_table(p, m, reinterpret_cast<int32_t *>(image.data() + good_off));

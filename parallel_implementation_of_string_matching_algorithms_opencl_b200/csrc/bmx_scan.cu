@@ -119,15 +119,40 @@ constexpr size_t kCtlBytes = (sizeof(SmemCtl) + 127) & ~size_t(127);
 // advance by one (:24); on a mismatch after k matched bytes advance by d1 = max(bad[T[i]]-k, 1)
 // (T[i] = byte under the LAST pattern position, :27-28) or max(d1, good[k]) when k > 0
 // (:29-31).  "Advance" here means: candidate bits inside the skipped range are dropped.
+// 4 bytes at byte offset `off` from a 4-byte aligned base (shared, global or generic memory), little endian.
+__device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t *base, int64_t off)
+{
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(base + (off & ~int64_t(3)));
+    return __funnelshift_r(w[0], w[1], 8 * (int)(off & 3));
+}
+
+// `wordwise` is set when the text is verified from the staged tile (whose halo makes the aligned word
+// pairs safe to read); long patterns verified from global memory compare byte by byte.
 __device__ __noinline__ uint32_t verify_candidates(uint32_t cand, const uint8_t *vbase, int64_t p0, int32_t m,
-                                                   const uint8_t *pat, const int32_t *bad, const int32_t *good)
+                                                   const uint8_t *pat, const int32_t *bad, const int32_t *good,
+                                                   bool wordwise)
 {
     uint32_t hits = 0;
     while (cand) {
         const int b = __ffs(cand) - 1;
-        const uint8_t *t = vbase + (p0 + b);
+        const int64_t p = p0 + b;
+        const uint8_t *t = vbase + p;
+        // k = number of pattern bytes that match from the right end (kernel1.cl:21-22), found four
+        // bytes at a time: in a little-endian word the rightmost text byte is the most significant one,
+        // so the leading zero bytes of the XOR are exactly the matched suffix bytes of that word.
         int32_t k = 0;
-        while (k < m && t[m - 1 - k] == pat[m - 1 - k]) ++k;
+        bool differs = false;
+        while (wordwise && k + 4 <= m) {
+            const uint32_t x = load_u32_unaligned(vbase, p + m - 4 - k) ^ load_u32_unaligned(pat, m - 4 - k);
+            if (x) {
+                k += __clz(x) >> 3;
+                differs = true;
+                break;
+            }
+            k += 4;
+        }
+        if (!differs)
+            while (k < m && t[m - 1 - k] == pat[m - 1 - k]) ++k;
         int32_t shift;
         if (k == m) {
             hits |= 1u << b;
@@ -323,7 +348,7 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
             if (!vc.all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
             any_cand |= cand;
             hm[sl] = 0;
-            if (cand) hm[sl] = vc.exact_filter ? cand : verify_candidates(cand, vc.vbase, p0, A.m, vc.pat, vc.bad, vc.good);
+            if (cand) hm[sl] = vc.exact_filter ? cand : verify_candidates(cand, vc.vbase, p0, A.m, vc.pat, vc.bad, vc.good, A.verify_smem != 0);
             seg_hits += __popc(hm[sl]);
         }
         cand_lanes += __popc(__ballot_sync(0xFFFFFFFFu, any_cand != 0));
@@ -473,7 +498,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                                 uint32_t cand = filter_mask<VARIANT, FULL8>(w[sl], w4[sl], A);
                                 if (!all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
                                 if (cand)
-                                    hm[sl] = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good);
+                                    hm[sl] = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good, A.verify_smem != 0);
                                 seg_hits += __popc(hm[sl]);
                             }
                         }
