@@ -58,6 +58,19 @@ def test_config1_ascii_64MiB_m16(bmx, oracle, dev):
     host = t.cpu().numpy()
     c2, p2 = bmx.search(host, pat)
     assert c2 == count and np.array_equal(p2, oracle.search_np(host, pat, threads=-1))
+    # and against the reference's OWN code (kernel1.cl + BoyreMoore.cpp tables through the shim), which is
+    # defined on this input (7-bit bytes, m <= 99, n < 2^31): the serial result, one partition {0, n-1}
+    import ctypes
+    from pathlib import Path
+    so = Path(__file__).resolve().parents[1] / "oracle" / "_ref" / "libref_bm.so"
+    if so.exists():
+        ref = ctypes.CDLL(str(so))
+        want = np.zeros(count + 16, dtype=np.int64)
+        rc_count = ctypes.c_uint64()
+        rc = ref.ref_bm_search(ctypes.c_void_p(host.ctypes.data), ctypes.c_int64(n), ctypes.c_char_p(pat), ctypes.c_int32(m),
+                               want.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(want.size), ctypes.byref(rc_count))
+        assert rc == 0 and rc_count.value == count
+        assert np.array_equal(want[:count], p2)
 
 
 def test_config2_dna_4GiB_m32(bmx, oracle, dev):

@@ -379,3 +379,37 @@ def test_mid_density_and_mixed_blocks(bmx, oracle, dev):
             assert count == want.size and np.array_equal(pos.cpu().numpy(), want[:cap]), (pat, "truncated")
             count, _, _ = bmx.search_device(td, pat)
             assert count == want.size
+
+
+def test_concurrent_host_threads_are_independent(bmx, oracle, dev):
+    """The convenience entry points keep per-thread state: searches for different patterns from
+    several host threads at once must not disturb each other (the reference is single-threaded;
+    the ABI promises re-entrancy per thread)."""
+    import threading
+
+    text = bmx.synth.fill_host(0, 4 << 20, 91, bmx.synth.ALPHABETS["dna"])
+    td = to_dev(text, dev)
+    pats = [text[o:o + m].tobytes() for o, m in [(100, 7), (5000, 9), (77777, 12), (123456, 33), (9, 3), (31, 5)]]
+    want = [oracle.search(text.tobytes(), p) for p in pats]
+    errors = []
+
+    def worker(i):
+        try:
+            for rep in range(6):
+                if rep % 2:
+                    with torch.cuda.stream(torch.cuda.Stream(device=dev)):
+                        c, pos, _ = bmx.search_device(td, pats[i], max_positions=want[i].size + 5)
+                        got = pos.cpu().numpy()
+                else:
+                    c, got = bmx.search(text, pats[i])
+                if c != want[i].size or not np.array_equal(got, want[i]):
+                    errors.append((i, rep, c, want[i].size))
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(len(pats))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
