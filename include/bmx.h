@@ -166,6 +166,11 @@ int bmx_scanner_begin(bmx_scanner *s, int64_t *d_pos_out, int64_t pos_cap, void 
  * No host synchronisation. */
 int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_base, void *stream);
 
+/* CUDA-event instrumentation of bmx_scanner_scan: 0 = none, 1 = the whole scan (device_ms), 2 = also the
+ * scan kernel alone (scan_kernel_ms; default).  Event records between back-to-back kernels cost about 10 us
+ * per scan on B200, so a throughput pipeline switches them off. */
+int bmx_scanner_set_timing(bmx_scanner *s, int level);
+
 /* Asynchronously packs the result for a collective into DEVICE memory d_dst on `stream`:
  * d_dst[0] = running count, d_dst[1] = positions actually written = min(count, pos_cap),
  * d_dst[2 .. 2+head) = the first `head` entries of the position buffer (entries beyond d_dst[1]

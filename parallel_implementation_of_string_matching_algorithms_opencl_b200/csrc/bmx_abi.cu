@@ -82,6 +82,7 @@ struct bmx_scanner {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     cudaEvent_t ev_k0 = nullptr, ev_k1 = nullptr;  // around the scan kernel alone
     bool timing_open = false;
+    int timing_level = 2;  // 0 none, 1 whole scan, 2 + scan kernel alone
     bmx_stats stats{};
 };
 
@@ -264,17 +265,17 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     a.carry_out = s->d_ctrl + ((s->scan_index + 1u) & 1u);
     a.count_acc = s->d_ctrl + 2;
 
-    if (!s->timing_open) {
+    if (s->timing_level >= 1 && !s->timing_open) {
         BMX_CUDA(cudaEventRecord(s->ev_start, st));
         s->timing_open = true;
     }
     BMX_CUDA(cudaMemsetAsync(s->d_scratch, 0, zero_bytes, st));
-    BMX_CUDA(cudaEventRecord(s->ev_k0, st));
+    if (s->timing_level >= 2) BMX_CUDA(cudaEventRecord(s->ev_k0, st));
     if (int rc = launch_scan(a, launch, s->positions, st)) return rc;
-    BMX_CUDA(cudaEventRecord(s->ev_k1, st));
+    if (s->timing_level >= 2) BMX_CUDA(cudaEventRecord(s->ev_k1, st));
     if (s->positions)
         if (int rc = launch_emit(a, st)) return rc;
-    BMX_CUDA(cudaEventRecord(s->ev_stop, st));
+    if (s->timing_level >= 1) BMX_CUDA(cudaEventRecord(s->ev_stop, st));
 
     s->scan_index += 1;
     s->stats.kernel_launches += s->positions ? 2 : 1;
@@ -283,6 +284,13 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     s->stats.tile_bytes = launch.tile_bytes;
     s->stats.smem_bytes = (int32_t)launch.smem_bytes;
     s->stats.tiles += a.num_tiles;
+    return BMX_OK;
+}
+
+int bmx_scanner_set_timing(bmx_scanner *s, int level)
+{
+    if (!s || level < 0 || level > 2) return fail(BMX_E_BADARG, "bmx_scanner_set_timing: level must be 0, 1 or 2");
+    s->timing_level = level;
     return BMX_OK;
 }
 
@@ -307,7 +315,8 @@ int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, vo
         float ms = 0.f;
         BMX_CUDA(cudaEventElapsedTime(&ms, s->ev_start, s->ev_stop));
         s->stats.device_ms = ms;
-        if (s->stats.kernel_launches > 0 && cudaEventElapsedTime(&ms, s->ev_k0, s->ev_k1) == cudaSuccess) s->stats.scan_kernel_ms = ms;
+        if (s->timing_level >= 2 && s->stats.kernel_launches > 0 && cudaEventElapsedTime(&ms, s->ev_k0, s->ev_k1) == cudaSuccess)
+            s->stats.scan_kernel_ms = ms;
     }
     if (stats) *stats = s->stats;
     return BMX_OK;

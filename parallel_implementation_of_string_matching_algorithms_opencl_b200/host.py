@@ -191,6 +191,10 @@ class Scanner:
     def scan(self, text, pos_base=0, stream=0):
         check(self._lib.bmx_scanner_scan(self._h, c_void_p(text.data_ptr()), text.numel(), c_int64(pos_base), c_void_p(stream)))
 
+    def set_timing(self, level: int):
+        """0: no CUDA events, 1: whole scan (device_ms), 2: also the scan kernel alone (default)."""
+        check(self._lib.bmx_scanner_set_timing(self._h, int(level)))
+
     def export_result(self, packed, stream=0):
         """Enqueue {count, positions written, first len(packed)-2 positions} into the int64 CUDA
         tensor `packed` (no host sync): the send buffer of the multi-GPU exchange step."""
