@@ -413,3 +413,36 @@ def test_concurrent_host_threads_are_independent(bmx, oracle, dev):
     for t in threads:
         t.join()
     assert not errors, errors
+
+
+def test_fuzz_all_densities_and_capacities(bmx, oracle, dev):
+    """Random, periodic and mixed texts from 1 byte to a few MiB over alphabets of 1..256 symbols: every
+    emission path (solo lane, warp-cooperative, staged, full segments, dense tickets) with full, halved
+    and single-entry capacities.  (profiles/stress_fuzz.py is the long-running version of this test.)"""
+    rnd = random.Random(2024)
+    rng = np.random.default_rng(2024)
+    for it in range(90):
+        sigma = rnd.choice([1, 2, 2, 3, 4, 8, 26, 256])
+        n = rnd.choice([rnd.randint(1, 4000), rnd.randint(4000, 300000), rnd.randint(300000, 3 << 20)])
+        off = 60 if sigma < 190 else 0
+        kind = rnd.choice(["random", "random", "periodic", "mixed"])
+        if kind == "periodic":
+            unit = bytes(rnd.randrange(sigma) + off for _ in range(rnd.randint(1, 7)))
+            text = np.frombuffer((unit * (n // len(unit) + 1))[:n], dtype=np.uint8).copy()
+        else:
+            text = (rng.integers(0, sigma, size=n, dtype=np.uint8) + off).astype(np.uint8)
+            if kind == "mixed" and n > 1000:
+                a, b = sorted(rnd.sample(range(n), 2))
+                text[a:b] = text[a]
+        m = min(rnd.choice([1, 2, 3, 4, 5, 7, 8, 10, 11, 16, 25, 33, 64, 128, 300]), n)
+        if rnd.random() < 0.7:
+            o = rnd.randint(0, n - m)
+            pat = text[o:o + m].tobytes()
+        else:
+            pat = bytes(rnd.randrange(sigma) + off for _ in range(m))
+        want = oracle.search_np(text, pat, threads=4) if n > 100000 else oracle.search(text.tobytes(), pat)
+        td = to_dev(text, dev, misalign=rnd.randint(0, 20))
+        for variant in VARIANTS_FOR(m):
+            cap = rnd.choice([max(n, 1), max(want.size // 2, 1), 1])
+            count, pos, _ = bmx.search_device(td, pat, max_positions=cap, variant=variant)
+            assert count == want.size and np.array_equal(pos.cpu().numpy(), want[:cap]), (it, kind, sigma, n, m, variant, cap)
