@@ -183,6 +183,23 @@ int bmx_scanner_export_result(bmx_scanner *s, void *d_dst /* int64[2 + head] */,
 int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, void *stream);
 
 /*
+ * Single-process multi-GPU search over HOST text (the reference has one device, BoyreMoore.cpp:217-219, and
+ * splits its text into word ranges WITHOUT overlap, :119-141).  GPU r of R receives the bytes
+ * [lo_r, hi_r + m - 1): it owns the match START positions [lo_r, hi_r) and reads an (m-1)-byte halo, so an
+ * occurrence straddling a seam is reported exactly once, with its global offset.  One host thread per GPU
+ * drives the chunked, overlapped ingest of its shard (every GPU uses its own PCIe link); counts are summed on
+ * the host and the per-shard lists are copied into pos_out in shard order, which is ascending.
+ * shard_counts (optional, ngpus entries) receives the per-GPU hit counts.  Same result as bmx_search.
+ * (One process per GPU with NCCL collectives is the other supported layout: distributed.py.)
+ */
+typedef struct bmx_mg bmx_mg;
+int bmx_mg_create(int ngpus /* <= 0: all visible GPUs */, bmx_mg **out);
+void bmx_mg_destroy(bmx_mg *mg);
+int bmx_mg_device_count(const bmx_mg *mg);
+int bmx_mg_search(bmx_mg *mg, const char *text, int64_t n, const char *pat, int32_t m,
+                  int64_t *pos_out, int64_t pos_cap, uint64_t *count_out, uint64_t *shard_counts);
+
+/*
  * Synthetic text generator used by the tests and bench.py (identical definition on the CPU in
  * oracle/bm_oracle.c:oracle_synth_fill): fills d_text[0..len) with the bytes at absolute
  * offsets [offset, offset+len) of the stream defined by (seed, alphabet[sigma]).

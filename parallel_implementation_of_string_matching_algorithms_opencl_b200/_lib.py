@@ -28,7 +28,7 @@ EXPORTS = [
     "bmx_version", "bmx_last_error", "bmx_device_count", "bmx_build_tables", "bmx_search",
     "bmx_search_ex", "bmx_search_device", "bmx_search_device_ex", "bmx_search_partitions",
     "bmx_scanner_create", "bmx_scanner_destroy", "bmx_scanner_set_pattern", "bmx_scanner_begin",
-    "bmx_scanner_scan", "bmx_scanner_finish", "bmx_scanner_export_result", "bmx_scanner_set_timing", "bmx_synth_fill_device", "bmx_partition_words",
+    "bmx_scanner_scan", "bmx_scanner_finish", "bmx_scanner_export_result", "bmx_scanner_set_timing", "bmx_mg_create", "bmx_mg_destroy", "bmx_mg_device_count", "bmx_mg_search", "bmx_synth_fill_device", "bmx_partition_words",
 ]
 
 
@@ -95,6 +95,12 @@ def load() -> ctypes.CDLL:
     lib.bmx_scanner_export_result.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     lib.bmx_scanner_finish.argtypes = [c_void_p, POINTER(c_uint64), POINTER(BmxStats), c_void_p]
     lib.bmx_partition_words.argtypes = [c_void_p, c_int64, c_int32, POINTER(c_int32)]
+    lib.bmx_mg_create.argtypes = [c_int, POINTER(c_void_p)]
+    lib.bmx_mg_destroy.argtypes = [c_void_p]
+    lib.bmx_mg_destroy.restype = None
+    lib.bmx_mg_device_count.argtypes = [c_void_p]
+    lib.bmx_mg_device_count.restype = c_int
+    lib.bmx_mg_search.argtypes = [c_void_p, c_void_p, c_int64, c_char_p, c_int32, c_void_p, c_int64, POINTER(c_uint64), POINTER(c_uint64)]
     lib.bmx_synth_fill_device.argtypes = [c_void_p, c_int64, c_int64, c_uint64, c_char_p, c_int32, c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)

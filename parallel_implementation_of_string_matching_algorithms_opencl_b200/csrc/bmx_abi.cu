@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <string>
 #include <thread>
 #include <vector>
 
@@ -436,19 +437,22 @@ int bmx_search_device(const void *d_text, int64_t n, const char *pat, int32_t m,
     return rc;
 }
 
-int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int32_t m, int64_t *pos_out,
-                  int64_t pos_cap, uint64_t *count_out, int32_t variant, bmx_stats *stats)
+}  // extern "C"
+
+namespace {
+
+// Host text -> device (chunked, overlapped with scanning) -> hits in a device buffer.  On success *d_pos_out
+// (when want_pos) is a stream-ordered allocation on c.scan_stream holding min(count, dev_cap) global
+// positions (start + pos_base); the caller copies it out and frees it with cudaFreeAsync(.., c.scan_stream).
+int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, const char *pat, int32_t m, int64_t pos_base,
+                    bool want_pos, int64_t dev_cap, int32_t variant, int64_t **d_pos_out, uint64_t *count_out, bmx_stats *stats)
 {
-    if (!count_out || !pat) return fail(BMX_E_BADARG, "bmx_search: pat/count_out must be non-NULL");
-    if (n < 0 || (!text && n > 0)) return fail(BMX_E_BADARG, "bmx_search: bad text (n=%lld)", (long long)n);
-    if (pos_cap < 0) return fail(BMX_E_BADARG, "pos_cap < 0");
-    if (m <= 0 || m > BMX_MAX_PATTERN)
-        return fail(BMX_E_BADARG, "pattern length %d outside 1..%d (an empty pattern is rejected)", m, BMX_MAX_PATTERN);
-    ThreadCtx *c = nullptr;
-    if (int rc = get_ctx(device, &c)) return rc;
+    ThreadCtx *c = &ctx;
     *count_out = 0;
+    if (d_pos_out) *d_pos_out = nullptr;
     if (stats) *stats = bmx_stats{};
     if (n < m) return BMX_OK;
+    BMX_CUDA(cudaSetDevice(device));
 
     int64_t chunk = (int64_t)64 << 20;
     if (const char *e = getenv("BMX_H2D_CHUNK_MB")) {
@@ -459,8 +463,7 @@ int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int3
     const int64_t nchunks = (n + chunk - 1) / chunk;
     if (int rc = ensure_streams(*c, device, (size_t)nchunks + kBounce + 1)) return rc;
 
-    const int64_t max_hits = n - m + 1;
-    const int64_t dev_cap = pos_out ? std::min(pos_cap, max_hits) : 0;
+    if (!want_pos) dev_cap = 0;
     unsigned char *d_text = nullptr;
     int64_t *d_pos = nullptr;
     int rc = BMX_OK;
@@ -528,7 +531,7 @@ int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int3
         const int64_t have = off + len;
         const int64_t span = have - scanned;
         if (span >= m) {
-            if ((rc = bmx_scanner_scan(c->scanner, d_text + scanned, span, scanned, c->scan_stream)) != BMX_OK) {
+            if ((rc = bmx_scanner_scan(c->scanner, d_text + scanned, span, pos_base + scanned, c->scan_stream)) != BMX_OK) {
                 cleanup();
                 return rc;
             }
@@ -543,14 +546,47 @@ int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int3
     }
     *count_out = count;
     if (stats) *stats = st;
-    const int64_t ncopy = std::min<int64_t>((int64_t)count, dev_cap);
-    if (ncopy > 0) {
-        BMX_TRY(cudaMemcpyAsync(pos_out, d_pos, (size_t)ncopy * 8, cudaMemcpyDeviceToHost, c->scan_stream));
-        BMX_TRY(cudaStreamSynchronize(c->scan_stream));
+    BMX_TRY(cudaFreeAsync(d_text, c->scan_stream));
+    d_text = nullptr;
+    if (d_pos_out) {
+        *d_pos_out = d_pos;
+    } else if (d_pos) {
+        cudaFreeAsync(d_pos, c->scan_stream);
     }
-    cleanup();
 #undef BMX_TRY
     return BMX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int32_t m, int64_t *pos_out,
+                  int64_t pos_cap, uint64_t *count_out, int32_t variant, bmx_stats *stats)
+{
+    if (!count_out || !pat) return fail(BMX_E_BADARG, "bmx_search: pat/count_out must be non-NULL");
+    if (n < 0 || (!text && n > 0)) return fail(BMX_E_BADARG, "bmx_search: bad text (n=%lld)", (long long)n);
+    if (pos_cap < 0) return fail(BMX_E_BADARG, "pos_cap < 0");
+    if (m <= 0 || m > BMX_MAX_PATTERN)
+        return fail(BMX_E_BADARG, "pattern length %d outside 1..%d (an empty pattern is rejected)", m, BMX_MAX_PATTERN);
+    ThreadCtx *c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    *count_out = 0;
+    if (stats) *stats = bmx_stats{};
+    if (n < m) return BMX_OK;
+    const int64_t dev_cap = pos_out ? std::min(pos_cap, n - m + 1) : 0;
+    int64_t *d_pos = nullptr;
+    if (int rc = ingest_and_scan(*c, device, text, n, pat, m, 0, dev_cap > 0, dev_cap, variant, &d_pos, count_out, stats)) return rc;
+    int rc = BMX_OK;
+    const int64_t ncopy = std::min<int64_t>((int64_t)*count_out, dev_cap);
+    if (ncopy > 0) {
+        cudaError_t e = cudaMemcpyAsync(pos_out, d_pos, (size_t)ncopy * 8, cudaMemcpyDeviceToHost, c->scan_stream);
+        if (e != cudaSuccess) rc = fail(BMX_E_CUDA, "position read-back: %s", cudaGetErrorString(e));
+    }
+    if (d_pos) cudaFreeAsync(d_pos, c->scan_stream);
+    const cudaError_t e = cudaStreamSynchronize(c->scan_stream);
+    if (rc == BMX_OK && e != cudaSuccess) rc = fail(BMX_E_CUDA, "bmx_search: %s", cudaGetErrorString(e));
+    return rc;
 }
 
 int bmx_search(const char *text, int64_t n, const char *pat, int32_t m, int64_t *pos_out, int64_t pos_cap,
@@ -658,6 +694,153 @@ int bmx_synth_fill_device(void *d_text, int64_t offset, int64_t len, uint64_t se
         return fail(BMX_E_BADARG, "bmx_synth_fill_device: bad argument");
     if (int rc = check_device(0)) return rc;
     return launch_synth_fill(d_text, offset, len, seed, alphabet, sigma, stream);
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// single-process multi-GPU search over host text: contiguous shards + (m-1)-byte halo,
+// one host thread per GPU for the ingest, positions gathered in shard order (= ascending)
+// ---------------------------------------------------------------------------------------------
+struct bmx_mg {
+    std::vector<int> devices;
+    std::vector<ThreadCtx *> ctx;
+};
+
+int bmx_mg_create(int ngpus, bmx_mg **out)
+{
+    if (!out) return fail(BMX_E_BADARG, "bmx_mg_create: out is NULL");
+    *out = nullptr;
+    if (int rc = check_device(0)) return rc;
+    int have = 0;
+    BMX_CUDA(cudaGetDeviceCount(&have));
+    if (ngpus <= 0) ngpus = have;
+    if (ngpus > have) return fail(BMX_E_BADARG, "bmx_mg_create: %d GPUs requested, %d visible", ngpus, have);
+    int keep = 0;
+    cudaGetDevice(&keep);
+    bmx_mg *mg = new (std::nothrow) bmx_mg();
+    if (!mg) return fail(BMX_E_NOMEM, "out of host memory");
+    for (int d = 0; d < ngpus; ++d) {
+        ThreadCtx *c = new (std::nothrow) ThreadCtx();
+        int rc = c ? BMX_OK : fail(BMX_E_NOMEM, "out of host memory");
+        if (rc == BMX_OK) rc = bmx_scanner_create(d, &c->scanner);
+        if (rc != BMX_OK) {
+            delete c;
+            bmx_mg_destroy(mg);
+            cudaSetDevice(keep);
+            return rc;
+        }
+        mg->devices.push_back(d);
+        mg->ctx.push_back(c);
+    }
+    cudaSetDevice(keep);
+    *out = mg;
+    return BMX_OK;
+}
+
+void bmx_mg_destroy(bmx_mg *mg)
+{
+    if (!mg) return;
+    int keep = 0;
+    cudaGetDevice(&keep);
+    for (size_t i = 0; i < mg->ctx.size(); ++i) {
+        ThreadCtx *c = mg->ctx[i];
+        cudaSetDevice(mg->devices[i]);
+        if (c->scanner) bmx_scanner_destroy(c->scanner);
+        if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+        if (c->scan_stream) cudaStreamDestroy(c->scan_stream);
+        for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+        for (int b = 0; b < kBounce; ++b)
+            if (c->bounce[b]) cudaFreeHost(c->bounce[b]);
+        delete c;
+    }
+    cudaSetDevice(keep);
+    delete mg;
+}
+
+int bmx_mg_device_count(const bmx_mg *mg) { return mg ? (int)mg->devices.size() : 0; }
+
+int bmx_mg_search(bmx_mg *mg, const char *text, int64_t n, const char *pat, int32_t m, int64_t *pos_out, int64_t pos_cap,
+                  uint64_t *count_out, uint64_t *shard_counts)
+{
+    if (!mg || !count_out || !pat) return fail(BMX_E_BADARG, "bmx_mg_search: NULL argument");
+    if (n < 0 || (!text && n > 0)) return fail(BMX_E_BADARG, "bmx_mg_search: bad text (n=%lld)", (long long)n);
+    if (pos_cap < 0) return fail(BMX_E_BADARG, "pos_cap < 0");
+    if (m <= 0 || m > BMX_MAX_PATTERN)
+        return fail(BMX_E_BADARG, "pattern length %d outside 1..%d (an empty pattern is rejected)", m, BMX_MAX_PATTERN);
+    const int R = (int)mg->devices.size();
+    *count_out = 0;
+    for (int r = 0; r < R && shard_counts; ++r) shard_counts[r] = 0;
+    if (n < m) return BMX_OK;
+
+    // rank r owns the START positions [lo_r, hi_r) and reads (m-1) bytes of halo behind hi_r
+    int64_t per = (n + R - 1) / R;
+    per = (per + 15) & ~int64_t(15);
+    struct Shard {
+        int64_t lo = 0, hi = 0, end = 0, cap = 0;
+        int64_t *d_pos = nullptr;
+        uint64_t count = 0;
+        int rc = BMX_OK;
+        std::string err;
+    };
+    std::vector<Shard> sh((size_t)R);
+    std::vector<std::thread> workers;
+    for (int r = 0; r < R; ++r) {
+        Shard &s = sh[(size_t)r];
+        s.lo = std::min<int64_t>(n, (int64_t)r * per);
+        s.hi = std::min<int64_t>(n, s.lo + per);
+        s.end = std::min<int64_t>(n, s.hi + m - 1);
+        s.cap = pos_out ? std::min<int64_t>(pos_cap, s.hi - s.lo) : 0;
+        if (s.end - s.lo < m) continue;
+        workers.emplace_back([&, r]() {
+            Shard &w = sh[(size_t)r];
+            w.rc = ingest_and_scan(*mg->ctx[(size_t)r], mg->devices[(size_t)r], text + w.lo, w.end - w.lo, pat, m, w.lo, w.cap > 0,
+                                   w.cap, BMX_VARIANT_AUTO, &w.d_pos, &w.count, nullptr);
+            if (w.rc != BMX_OK) w.err = bmx_last_error();
+        });
+    }
+    for (auto &t : workers) t.join();
+
+    int rc = BMX_OK;
+    std::string err;
+    uint64_t total = 0;
+    for (int r = 0; r < R; ++r) {
+        if (sh[(size_t)r].rc != BMX_OK && rc == BMX_OK) {
+            rc = sh[(size_t)r].rc;
+            err = sh[(size_t)r].err;
+        }
+        total += sh[(size_t)r].count;
+        if (shard_counts) shard_counts[r] = sh[(size_t)r].count;
+    }
+    // gather: shard lists are ascending and shards are ordered, so concatenation is the sorted result
+    int keep = 0;
+    cudaGetDevice(&keep);
+    int64_t off = 0;
+    for (int r = 0; r < R; ++r) {
+        Shard &s = sh[(size_t)r];
+        cudaSetDevice(mg->devices[(size_t)r]);
+        cudaStream_t st = mg->ctx[(size_t)r]->scan_stream;
+        if (rc == BMX_OK && s.d_pos) {
+            const int64_t have = std::min<int64_t>((int64_t)s.count, s.cap);
+            const int64_t ncopy = std::max<int64_t>(0, std::min<int64_t>(have, pos_cap - off));
+            if (ncopy > 0 && cudaMemcpyAsync(pos_out + off, s.d_pos, (size_t)ncopy * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) {
+                rc = BMX_E_CUDA;
+                err = "position gather failed";
+            }
+        }
+        off += (int64_t)s.count;
+        if (s.d_pos) cudaFreeAsync(s.d_pos, st);
+    }
+    for (int r = 0; r < R; ++r) {
+        cudaSetDevice(mg->devices[(size_t)r]);
+        if (mg->ctx[(size_t)r]->scan_stream && cudaStreamSynchronize(mg->ctx[(size_t)r]->scan_stream) != cudaSuccess && rc == BMX_OK) {
+            rc = BMX_E_CUDA;
+            err = "stream synchronisation failed";
+        }
+    }
+    cudaSetDevice(keep);
+    if (rc != BMX_OK) return fail(rc, "bmx_mg_search: %s", err.c_str());
+    *count_out = total;
+    return BMX_OK;
 }
 
 }  // extern "C"

@@ -205,3 +205,38 @@ class Scanner:
         stats = BmxStats()
         check(self._lib.bmx_scanner_finish(self._h, ctypes.byref(count), ctypes.byref(stats), c_void_p(stream)))
         return count.value, stats.as_dict()
+
+
+class MultiGpu:
+    """Single-process multi-GPU search over host text (bmx_mg_*): shards + (m-1) halo, one host thread per GPU."""
+
+    def __init__(self, ngpus: int = 0):
+        self._lib = _lib.load()
+        self._h = c_void_p()
+        check(self._lib.bmx_mg_create(ngpus, ctypes.byref(self._h)))
+        self.ngpus = self._lib.bmx_mg_device_count(self._h)
+
+    def close(self):
+        if self._h:
+            self._lib.bmx_mg_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def search(self, text, pattern, max_positions: int | None = None):
+        """(count, positions, per_gpu_counts) -- the serial-reference result, like search()."""
+        pat = _as_bytes(pattern)
+        ptr, n, keep = _host_text(text)
+        if max_positions is None:
+            max_positions = max(n - len(pat) + 1, 0)
+        pos = np.empty(max_positions, dtype=np.int64)
+        count = c_uint64(0)
+        shard = (c_uint64 * self.ngpus)()
+        check(self._lib.bmx_mg_search(self._h, ptr, n, pat, len(pat), pos.ctypes.data if max_positions else None,
+                                      max_positions, ctypes.byref(count), shard))
+        del keep
+        return count.value, pos[: min(count.value, max_positions)], [int(x) for x in shard]

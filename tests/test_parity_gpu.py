@@ -446,3 +446,27 @@ def test_fuzz_all_densities_and_capacities(bmx, oracle, dev):
             cap = rnd.choice([max(n, 1), max(want.size // 2, 1), 1])
             count, pos, _ = bmx.search_device(td, pat, max_positions=cap, variant=variant)
             assert count == want.size and np.array_equal(pos.cpu().numpy(), want[:cap]), (it, kind, sigma, n, m, variant, cap)
+
+
+def test_single_process_multi_gpu_entry_point(bmx, oracle, dev):
+    """bmx_mg_search on however many GPUs are visible (1 on the test box; the shard logic is the same
+    and profiles/mg_check.py exercises it on 2+): seam-straddling plants, capacities, count-only."""
+    text = bmx.synth.fill_host(0, (9 << 20) + 77, 55, bmx.synth.ALPHABETS["dna"])
+    m = 11
+    pat = text[3000:3000 + m].tobytes()
+    for ngpus in (1, 0):
+        mg = bmx.MultiGpu(ngpus)
+        per = -(-text.size // mg.ngpus)
+        per = -(-per // 16) * 16
+        t2 = text.copy()
+        seams = [r * per for r in range(1, mg.ngpus)]
+        bmx.synth.plant_host(t2, pat, [s - d for s in seams for d in (m // 2, 1, m - 1, m, 0)])
+        want = oracle.search_np(t2, pat, threads=4)
+        count, pos, shard = mg.search(t2, pat)
+        assert count == want.size == sum(shard) and np.array_equal(pos, want)
+        count, pos, _ = mg.search(t2, pat, max_positions=7)
+        assert count == want.size and np.array_equal(pos, want[:7])
+        count, pos, _ = mg.search(t2, pat, max_positions=0)
+        assert count == want.size and pos.size == 0
+        assert mg.search(b"ab", b"abc")[0] == 0
+        mg.close()
