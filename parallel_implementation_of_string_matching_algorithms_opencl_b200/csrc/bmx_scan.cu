@@ -35,6 +35,9 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <cstdlib>
 #include <cstring>
 
@@ -1032,11 +1035,28 @@ static const void *pick_kernel(int variant, bool full8, int tile, bool positions
 
 int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, ScanLaunch *out)
 {
-    int sm_count = 0, smem_optin = 0, smem_sm = 0;
-    if (cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
-        cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
-        cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device) != cudaSuccess)
-        return fail(BMX_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+    // device attributes are queried once per device (a search on a 500 KB text is launch-latency bound)
+    struct DevInfo {
+        int sm_count = 0, smem_optin = 0, smem_sm = 0;
+    };
+    static DevInfo dev_info[64];
+    static std::mutex dev_mutex;
+    int sm_count, smem_optin, smem_sm;
+    {
+        std::lock_guard<std::mutex> lock(dev_mutex);
+        DevInfo &di = dev_info[device & 63];
+        if (di.sm_count == 0) {
+            if (cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+                cudaDeviceGetAttribute(&di.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
+                cudaDeviceGetAttribute(&di.smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device) != cudaSuccess) {
+                di = DevInfo{};
+                return fail(BMX_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+        }
+        sm_count = di.sm_count;
+        smem_optin = di.smem_optin;
+        smem_sm = di.smem_sm;
+    }
 
     int tile = env_int("BMX_TILE", 32768);   // profiles/tune_knobs.py: 32 KiB tiles, 2 CTAs/SM, 3 stages
     if (tile != 16384 && tile != 32768) tile = 32768;
@@ -1072,9 +1092,18 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     const bool full8 = variant == BMX_VARIANT_WINDOW ? a->mulc == 1u : a->mask2 == 0xFFFFFFFFu;
     const void *k = pick_kernel(variant, full8, tile, positions);
     if (!k) return fail(BMX_E_BADARG, "no kernel for variant %d tile %d", variant, tile);
-    if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem_bytes) != cudaSuccess)
-        return fail(BMX_E_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", out->smem_bytes,
-                    cudaGetErrorString(cudaGetLastError()));
+    {
+        // the opt-in shared-memory limit of a kernel is raised once per (device, kernel, size)
+        static std::map<std::pair<int, const void *>, size_t> granted;
+        std::lock_guard<std::mutex> lock(dev_mutex);
+        size_t &have = granted[std::make_pair(device, k)];
+        if (have < out->smem_bytes) {
+            if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)out->smem_bytes) != cudaSuccess)
+                return fail(BMX_E_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", out->smem_bytes,
+                            cudaGetErrorString(cudaGetLastError()));
+            have = out->smem_bytes;
+        }
+    }
     return BMX_OK;
 }
 
@@ -1093,9 +1122,11 @@ int launch_emit(const ScanArgs &a, void *stream)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     cudaError_t e;
-    int dev = 0, sms = 148;
+    static int sms_cache[64];
+    int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int &sms = sms_cache[dev & 63];
+    if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
     const uint32_t items = a.num_blocks * kExpandSplit;
     const uint32_t grid = std::min<uint32_t>((items + kExpandWarps - 1) / kExpandWarps, (uint32_t)sms * 5u);  // one warp per item
     expand_kernel<<<grid, kExpandThreads, 0, st>>>(a);
