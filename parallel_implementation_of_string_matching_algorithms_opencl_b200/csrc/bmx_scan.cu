@@ -35,11 +35,11 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 #include <map>
 #include <mutex>
 #include <utility>
-#include <cstdlib>
-#include <cstring>
 
 #include "bmx_internal.h"
 
@@ -87,9 +87,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // global -> shared bulk copy (TMA, 1-D): bytes % 16 == 0, both addresses 16-byte aligned.
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
 {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+    // the text is streamed exactly once: mark its lines evict-first so they do not push the emission
+    // scratch (segment counts, masks) out of L2
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
                      smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
                  : "memory");
 }
 // Barrier over the consumer threads only (the producer warp has its own life cycle).
