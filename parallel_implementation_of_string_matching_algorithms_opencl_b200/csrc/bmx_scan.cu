@@ -25,7 +25,7 @@
 //
 // Filters (bmx_variant):
 //   QGRAM    m >= 7.  Any occurrence covers the aligned 32-bit word at ceil(p/4)*4 and the word
-//            after it; h = W[j] + K * (W[j+1] & mask2) is compared with the 4 pattern hashes for
+//            after it; h = W[j] + hmul * W[j+1] is compared with the 4 pattern hashes for
 //            r = (4 - p%4)%4.  1 IMAD + 4 ISETP per 4 text bytes, no funnel shifts.
 //   WINDOW   any m.  The <=4-byte window at every position (funnel shifts) against P[0..q).
 //            Exact for m <= 4.
@@ -202,17 +202,19 @@ __device__ __forceinline__ uint32_t window_at(uint32_t lo, uint32_t hi, int s, c
     return s == 0 ? lo : __funnelshift_r(lo, hi, 8 * s);
 }
 
-// FLAG: QGRAM -> the second word is used in full (m >= 11); WINDOW -> q == 4 (m >= 4).
+// FLAG: WINDOW -> q == 4 (m >= 4), no multiply needed; unused by QGRAM.
 template <int VARIANT, bool FLAG>
 __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const ScanArgs &A)
 {
     if (VARIANT == kQgram) {
         const uint32_t f0 = A.f[0], f1 = A.f[1], f2 = A.f[2], f3 = A.f[3];
-        const uint32_t m2 = A.mask2;
-        const uint32_t h0 = w.x + kHashMul * (FLAG ? w.y : (w.y & m2));
-        const uint32_t h1 = w.y + kHashMul * (FLAG ? w.z : (w.z & m2));
-        const uint32_t h2 = w.z + kHashMul * (FLAG ? w.w : (w.w & m2));
-        const uint32_t h3 = w.w + kHashMul * (FLAG ? w4 : (w4 & m2));
+        // hmul = K << (32 - 8*q2): the multiplication itself drops the bytes of the second word that lie
+        // beyond the q-gram (7 <= m <= 10), so short patterns need no masking instruction
+        const uint32_t km = A.hmul;
+        const uint32_t h0 = w.x + km * w.y;
+        const uint32_t h1 = w.y + km * w.z;
+        const uint32_t h2 = w.z + km * w.w;
+        const uint32_t h3 = w.w + km * w4;
         bool any = (h0 == f0) | (h0 == f1) | (h0 == f2) | (h0 == f3);
         any |= (h1 == f0) | (h1 == f1) | (h1 == f2) | (h1 == f3);
         any |= (h2 == f0) | (h2 == f1) | (h2 == f2) | (h2 == f3);
@@ -242,7 +244,7 @@ __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, con
     if (VARIANT == kQgram) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t h = ww[j] + kHashMul * (FLAG ? ww[j + 1] : (ww[j + 1] & A.mask2));
+            const uint32_t h = ww[j] + A.hmul * ww[j + 1];
             // word j with residue r flags start position 4j - r, i.e. bit 4j + 3 - r (bit 0 = c - 3)
 #pragma unroll
             for (int r = 0; r < 4; ++r) mask |= (uint32_t)(h == A.f[r]) << (4 * j + 3 - r);
@@ -991,7 +993,7 @@ static uint32_t le_word(const unsigned char *p, int nbytes)
 void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, ScanArgs *a)
 {
     a->f[0] = a->f[1] = a->f[2] = a->f[3] = 0;
-    a->mask2 = 0xFFFFFFFFu;
+    a->hmul = kHashMul;
     a->mulc = 1u;
     a->shl[0] = 1u << 24;   // multiplier that shifts a word right by 8 (high half) / left by 24 (low half)
     a->shl[1] = 1u << 16;
@@ -999,8 +1001,8 @@ void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, Sca
     if (variant == BMX_VARIANT_QGRAM) {
         const int q = std::min(m - 3, 8);  // every residue r = 0..3 sees q pattern bytes
         const int q2 = q - 4;              // bytes taken from the second word
-        a->mask2 = q2 >= 4 ? 0xFFFFFFFFu : ((1u << (8 * q2)) - 1u);
-        for (int r = 0; r < 4; ++r) a->f[r] = le_word(pat + r, 4) + kHashMul * le_word(pat + r + 4, q2);
+        a->hmul = q2 >= 4 ? kHashMul : (q2 == 0 ? 0u : (kHashMul << (32 - 8 * q2)));
+        for (int r = 0; r < 4; ++r) a->f[r] = le_word(pat + r, 4) + a->hmul * le_word(pat + r + 4, q2);
     } else if (variant == BMX_VARIANT_WINDOW) {
         const int q = std::min(m, 4);
         a->mulc = q >= 4 ? 1u : (1u << (32 - 8 * q));
@@ -1017,10 +1019,8 @@ static const void *kernel_ptr()
 template <int TILE>
 static const void *pick_kernel_tile(int variant, bool full8, bool positions)
 {
-    if (variant == BMX_VARIANT_QGRAM) {
-        if (full8) return positions ? kernel_ptr<kQgram, true, TILE, true>() : kernel_ptr<kQgram, true, TILE, false>();
-        return positions ? kernel_ptr<kQgram, false, TILE, true>() : kernel_ptr<kQgram, false, TILE, false>();
-    }
+    if (variant == BMX_VARIANT_QGRAM)
+        return positions ? kernel_ptr<kQgram, true, TILE, true>() : kernel_ptr<kQgram, true, TILE, false>();
     if (variant == BMX_VARIANT_WINDOW) {
         if (full8) return positions ? kernel_ptr<kWindow, true, TILE, true>() : kernel_ptr<kWindow, true, TILE, false>();
         return positions ? kernel_ptr<kWindow, false, TILE, true>() : kernel_ptr<kWindow, false, TILE, false>();
@@ -1093,7 +1093,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     const int spare = std::max(0, std::min(sm_count - 1, env_int("BMX_SPARE_SMS", 0)));
     out->grid = (int)std::min<int64_t>(tiles, (int64_t)(sm_count - spare) * ctas_per_sm);
 
-    const bool full8 = variant == BMX_VARIANT_WINDOW ? a->mulc == 1u : a->mask2 == 0xFFFFFFFFu;
+    const bool full8 = variant == BMX_VARIANT_WINDOW ? a->mulc == 1u : true;
     const void *k = pick_kernel(variant, full8, tile, positions);
     if (!k) return fail(BMX_E_BADARG, "no kernel for variant %d tile %d", variant, tile);
     {
@@ -1113,7 +1113,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
 
 int launch_scan(const ScanArgs &a, const ScanLaunch &l, bool positions, void *stream)
 {
-    const bool full8 = l.variant == BMX_VARIANT_WINDOW ? a.mulc == 1u : a.mask2 == 0xFFFFFFFFu;
+    const bool full8 = l.variant == BMX_VARIANT_WINDOW ? a.mulc == 1u : true;
     const void *k = pick_kernel(l.variant, full8, l.tile_bytes, positions);
     void *params[] = {const_cast<ScanArgs *>(&a)};
     const cudaError_t e = cudaLaunchKernel(k, dim3((unsigned)l.grid), dim3(kThreads), params, l.smem_bytes,
