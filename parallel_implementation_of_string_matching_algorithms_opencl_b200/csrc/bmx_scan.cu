@@ -202,7 +202,7 @@ __device__ __forceinline__ uint32_t window_at(uint32_t lo, uint32_t hi, int s, c
     return s == 0 ? lo : __funnelshift_r(lo, hi, 8 * s);
 }
 
-// FLAG: WINDOW -> q == 4 (m >= 4), no multiply needed; unused by QGRAM.
+// FLAG: WINDOW -> q == 4 (m >= 4), no multiply needed; QGRAM -> one hash multiplier for all four residues.
 template <int VARIANT, bool FLAG>
 __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const ScanArgs &A)
 {
@@ -210,6 +210,19 @@ __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const Sc
         const uint32_t f0 = A.f[0], f1 = A.f[1], f2 = A.f[2], f3 = A.f[3];
         // hmul = K << (32 - 8*q2): the multiplication itself drops the bytes of the second word that lie
         // beyond the q-gram (7 <= m <= 10), so short patterns need no masking instruction
+        if (!FLAG) {
+            // 7 <= m <= 10: residue r may use min(8, m - r) pattern bytes, so each residue hashes with its
+            // own multiplier -- 3 more IMADs per word, several times fewer candidates on small alphabets
+            const uint32_t k0 = A.hmulr[0], k1 = A.hmulr[1], k2 = A.hmulr[2], k3 = A.hmulr[3];
+            const uint32_t ww[5] = {w.x, w.y, w.z, w.w, w4};
+            bool any = false;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                any |= (ww[j] + k0 * ww[j + 1] == f0) | (ww[j] + k1 * ww[j + 1] == f1);
+                any |= (ww[j] + k2 * ww[j + 1] == f2) | (ww[j] + k3 * ww[j + 1] == f3);
+            }
+            return any;
+        }
         const uint32_t km = A.hmul;
         const uint32_t h0 = w.x + km * w.y;
         const uint32_t h1 = w.y + km * w.z;
@@ -247,7 +260,10 @@ __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, con
             const uint32_t h = ww[j] + A.hmul * ww[j + 1];
             // word j with residue r flags start position 4j - r, i.e. bit 4j + 3 - r (bit 0 = c - 3)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) mask |= (uint32_t)(h == A.f[r]) << (4 * j + 3 - r);
+            for (int r = 0; r < 4; ++r) {
+                const uint32_t hr = FLAG ? h : ww[j] + A.hmulr[r] * ww[j + 1];
+                mask |= (uint32_t)(hr == A.f[r]) << (4 * j + 3 - r);
+            }
         }
     } else {
 #pragma unroll
@@ -999,15 +1015,43 @@ void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, Sca
     a->shl[1] = 1u << 16;
     a->shl[2] = 1u << 8;
     if (variant == BMX_VARIANT_QGRAM) {
-        const int q = std::min(m - 3, 8);  // every residue r = 0..3 sees q pattern bytes
-        const int q2 = q - 4;              // bytes taken from the second word
-        a->hmul = q2 >= 4 ? kHashMul : (q2 == 0 ? 0u : (kHashMul << (32 - 8 * q2)));
-        for (int r = 0; r < 4; ++r) a->f[r] = le_word(pat + r, 4) + a->hmul * le_word(pat + r + 4, q2);
+        // residue r (pattern byte r on a word boundary) can use min(8, m - r) pattern bytes; for m >= 11
+        // that is 8 for every residue and one multiplier serves all four (a->hmul, the FULL8 kernels)
+        for (int r = 0; r < 4; ++r) {
+            const int q2 = std::min(m - r, 8) - 4;   // bytes taken from the second word
+            a->hmulr[r] = q2 >= 4 ? kHashMul : (q2 == 0 ? 0u : (kHashMul << (32 - 8 * q2)));
+            a->f[r] = le_word(pat + r, 4) + a->hmulr[r] * le_word(pat + r + 4, q2);
+        }
+        a->hmul = a->hmulr[3];
+        // Per-residue lengths cost 3 more IMADs per word: measured -6 % on large alphabets, where the
+        // shortest length is selective enough anyway, and +35 % / +32 % / +11 % on 4-letter text at m = 7 / 8 /
+        // 9 (profiles/short_qgram_r01.txt).  The text's alphabet is unknown here; the pattern's is the proxy.
+        bool seen[256] = {false};
+        int distinct = 0;
+        for (int i = 0; i < m && i < 16; ++i)
+            if (!seen[pat[i]]) { seen[pat[i]] = true; ++distinct; }
+        const int knob = env_int("BMX_QGRAM_UNIFORM", -1);   // measurement knob: 1 / 0 force one / four lengths
+        const bool uniform = knob >= 0 ? knob != 0 : !(m <= 9 && distinct <= 4);
+        if (uniform) {
+            for (int r = 0; r < 4; ++r) {
+                a->hmulr[r] = a->hmul;
+                a->f[r] = le_word(pat + r, 4) + a->hmul * le_word(pat + r + 4, std::min(m - 3, 8) - 4);
+            }
+        }
     } else if (variant == BMX_VARIANT_WINDOW) {
         const int q = std::min(m, 4);
         a->mulc = q >= 4 ? 1u : (1u << (32 - 8 * q));
         a->f[0] = le_word(pat, q) * a->mulc;
     }
+}
+
+// FULL8: WINDOW compares whole 4-byte windows (m >= 4); QGRAM hashes all residues with one multiplier.
+static bool uses_full8(int variant, const ScanArgs &a)
+{
+    if (variant == BMX_VARIANT_WINDOW) return a.mulc == 1u;
+    if (variant == BMX_VARIANT_QGRAM)
+        return a.hmulr[0] == a.hmulr[3] && a.hmulr[1] == a.hmulr[3] && a.hmulr[2] == a.hmulr[3];
+    return true;
 }
 
 template <int VARIANT, bool FULL8, int TILE, bool POSITIONS>
@@ -1019,8 +1063,10 @@ static const void *kernel_ptr()
 template <int TILE>
 static const void *pick_kernel_tile(int variant, bool full8, bool positions)
 {
-    if (variant == BMX_VARIANT_QGRAM)
-        return positions ? kernel_ptr<kQgram, true, TILE, true>() : kernel_ptr<kQgram, true, TILE, false>();
+    if (variant == BMX_VARIANT_QGRAM) {
+        if (full8) return positions ? kernel_ptr<kQgram, true, TILE, true>() : kernel_ptr<kQgram, true, TILE, false>();
+        return positions ? kernel_ptr<kQgram, false, TILE, true>() : kernel_ptr<kQgram, false, TILE, false>();
+    }
     if (variant == BMX_VARIANT_WINDOW) {
         if (full8) return positions ? kernel_ptr<kWindow, true, TILE, true>() : kernel_ptr<kWindow, true, TILE, false>();
         return positions ? kernel_ptr<kWindow, false, TILE, true>() : kernel_ptr<kWindow, false, TILE, false>();
@@ -1093,7 +1139,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     const int spare = std::max(0, std::min(sm_count - 1, env_int("BMX_SPARE_SMS", 0)));
     out->grid = (int)std::min<int64_t>(tiles, (int64_t)(sm_count - spare) * ctas_per_sm);
 
-    const bool full8 = variant == BMX_VARIANT_WINDOW ? a->mulc == 1u : true;
+    const bool full8 = uses_full8(variant, *a);
     const void *k = pick_kernel(variant, full8, tile, positions);
     if (!k) return fail(BMX_E_BADARG, "no kernel for variant %d tile %d", variant, tile);
     {
@@ -1113,7 +1159,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
 
 int launch_scan(const ScanArgs &a, const ScanLaunch &l, bool positions, void *stream)
 {
-    const bool full8 = l.variant == BMX_VARIANT_WINDOW ? a.mulc == 1u : true;
+    const bool full8 = uses_full8(l.variant, a);
     const void *k = pick_kernel(l.variant, full8, l.tile_bytes, positions);
     void *params[] = {const_cast<ScanArgs *>(&a)};
     const cudaError_t e = cudaLaunchKernel(k, dim3((unsigned)l.grid), dim3(kThreads), params, l.smem_bytes,

@@ -94,6 +94,30 @@ def test_fuzz_small_alphabets_all_variants(bmx, oracle, dev):
             assert count == want.size and np.array_equal(got, want), (it, sigma, n, m, variant)
 
 
+def test_short_qgram_both_hash_layouts(bmx, oracle, dev, monkeypatch):
+    """7 <= m <= 10: QGRAM hashes either one q-gram length for all four residues or min(8, m - r) bytes
+    per residue (chosen from the pattern's alphabet).  Both layouts, forced through the measurement knob,
+    must give the serial result on small and large alphabets."""
+    rnd = random.Random(77)
+    for it in range(120):
+        sigma = rnd.choice([1, 2, 4, 6, 26, 200])
+        n = rnd.randint(8, 50000)
+        m = rnd.choice([7, 8, 9, 10, 11])
+        text = bytes(rnd.randrange(40, 40 + sigma) for _ in range(n))
+        o = rnd.randint(0, max(n - m, 0))
+        pat = text[o:o + m] if n >= m and rnd.random() < 0.7 else bytes(rnd.randrange(40, 40 + sigma) for _ in range(m))
+        want = oracle.search(text, pat)
+        td = to_dev(text, dev, misalign=rnd.randint(0, 17))
+        for knob in ("0", "1", None):
+            if knob is None:
+                monkeypatch.delenv("BMX_QGRAM_UNIFORM", raising=False)
+            else:
+                monkeypatch.setenv("BMX_QGRAM_UNIFORM", knob)
+            count, got, stats = gpu_positions(bmx, td, pat, "qgram")
+            assert stats["variant"] == "qgram"
+            assert count == want.size and np.array_equal(got, want), (it, sigma, n, m, knob)
+
+
 def test_edge_cases(bmx, oracle, dev):
     E = bmx._lib
     # m > n: not an error, count 0 (kernel1.cl:15,19); empty text
