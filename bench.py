@@ -7,7 +7,7 @@
 One "step" = one pass of the hot path over one batch of synthetic text:
   N = 1   workload dna_m32_4GiB      (BASELINE.json configs[1]: 4 GiB random DNA, m = 32)
   N > 1   workload ascii95_m64_shard (configs[4]: 8 GiB per GPU of 95-symbol ASCII, m = 64,
-                                      sharded with (m-1) halo, counts all-reduced and position
+                                      sharded with (m-1) halo, counts and position
                                       lists gathered to rank 0 over NCCL) -- weak scaling.
 `value`  : device-resident text, CUDA-event timed, K back-to-back scans (positions written).
 `e2e`    : the same scan through the host-pointer C-ABI call bmx_search_ex: pinned host text,
@@ -194,7 +194,7 @@ def run_ours(args):
     scanner = bmx.Scanner(local)
     scanner.set_pattern(pat, variant=args.variant, stream=stream)
 
-    # N > 1: the exchange of step i (count all-reduce + all-gather of the position lists, NCCL) is
+    # N > 1: the exchange of step i (one all-gather of counts + position lists, NCCL) is
     # enqueued behind scan i and awaited only after the next scans have been queued, so the GPUs
     # always have a scan to run while the tiny collectives and their host sync complete.
     depth = 3 if world > 1 else 1

@@ -6,10 +6,10 @@ straddle a seam (BoyreMoore.cpp:119-141).  Here rank r owns the m
 positions [lo_r, hi_r) and reads (m-1) bytes of halo behind hi_r, so every occurrence is reported
 exactly once by the rank that owns its start, with its global offset (pos_base = lo_r).
 
-Exchange step (the only collectives on the path): all_reduce(sum) of the hit counts and ONE
-all_gather carrying each rank's count and (the head of) its position list; rank 0 concatenates
-the lists in rank order, which is already globally ascending.  Longer lists send their tail to
-rank 0 point-to-point.  Over NCCL this runs on NVLink/NVSwitch; the same
+Exchange step (the only collective on the path): ONE all_gather carrying each rank's count and
+(the head of) its position list; every rank sums the counts, rank 0 concatenates the lists in
+rank order, which is already globally ascending.  Longer lists send their tail to rank 0
+point-to-point.  Over NCCL this runs on NVLink/NVSwitch; the same
 code runs over gloo on CPU tensors in the tests.
 """
 from __future__ import annotations
@@ -36,8 +36,8 @@ def shard_read_range(n_total: int, m: int, lo: int, hi: int) -> tuple[int, int]:
 class PendingExchange:
     """Collectives of one exchange step, enqueued but not yet awaited (see combine_hits_start)."""
 
-    def __init__(self, works, total, everyone, width, fast_cap, positions_local, group, dst, device):
-        self.works, self.total, self.everyone = works, total, everyone
+    def __init__(self, works, everyone, width, fast_cap, positions_local, group, dst, device):
+        self.works, self.everyone = works, everyone
         self.width, self.fast_cap, self.positions_local = width, fast_cap, positions_local
         self.group, self.dst, self.device = group, dst, device
 
@@ -59,7 +59,7 @@ class PendingExchange:
                 w.wait()
             world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
             table = self.everyone.view(world, self.width)
-            header_dev = torch.cat([table[:, :2].reshape(-1), self.total])
+            header_dev = table[:, :2].reshape(-1)
             if cuda:
                 header = torch.empty(header_dev.numel(), dtype=torch.int64, pin_memory=True)
                 header.copy_(header_dev, non_blocking=True)
@@ -69,7 +69,7 @@ class PendingExchange:
             header = header.tolist()
             counts_host = [int(header[2 * r]) for r in range(world)]
             held_host = [int(header[2 * r + 1]) for r in range(world)]
-            total_host = int(header[-1])
+            total_host = sum(counts_host)                              # every rank holds every count
             fast_cap, pos = self.fast_cap, self.positions_local
 
             gathered = None
@@ -126,9 +126,9 @@ def combine_hits_start(count_local, positions_local, *, group=None, device=None,
     case count_local is ignored, positions_local is the whole output buffer, and nothing here waits
     for the scan: the collectives are enqueued behind it.
 
-    One all-gather carries every rank's [count, list length, first fast_cap positions]; the
-    all-reduce of the counts is enqueued next to it.  PendingExchange.finish() awaits both with a
-    single host synchronisation; lists longer than fast_cap (dense texts) send their remainder to
+    One all-gather carries every rank's [count, list length, first fast_cap positions] (the global
+    count is the sum of the gathered counts: no separate all-reduce).  PendingExchange.finish() awaits it
+    with a single host synchronisation; lists longer than fast_cap (dense texts) send their remainder to
     `dst` point-to-point.  Rank-order concatenation on `dst` is globally ascending: nothing is sorted.
     """
     import torch
@@ -148,14 +148,13 @@ def combine_hits_start(count_local, positions_local, *, group=None, device=None,
         assert packed.numel() == width and packed.dtype == torch.int64
         mine = packed
 
-    total = mine[:1].clone()
-    works = [dist.all_reduce(total, op=dist.ReduceOp.SUM, group=group, async_op=True)]   # global hit count
+    works = []
     everyone = torch.empty(world * width, dtype=torch.int64, device=device)
     try:
         works.append(dist.all_gather_into_tensor(everyone, mine, group=group, async_op=True))
     except (RuntimeError, NotImplementedError):
         _all_gather_list(everyone, mine, group)
-    return PendingExchange(works, total, everyone, width, fast_cap, positions_local, group, dst, device)
+    return PendingExchange(works, everyone, width, fast_cap, positions_local, group, dst, device)
 
 
 def combine_hits(count_local, positions_local, **kw):

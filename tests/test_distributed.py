@@ -1,4 +1,4 @@
-"""CPU, world_size 2 and 3 over gloo: the N>1 host logic (shard ownership, halo, count all-reduce,
+"""CPU, world_size 2 and 3 over gloo: the N>1 host logic (shard ownership, halo, count exchange,
 position gather to rank 0).  The local scan is injected -- here the oracle plays the device -- so
 the exchange code that runs over NCCL on the GPU box is the code exercised here."""
 from __future__ import annotations
