@@ -72,7 +72,7 @@ struct bmx_scanner {
     size_t d_block_cap = 0;
     ScanArgs proto{};         // filter constants + pattern pointers
     // result state
-    unsigned long long *d_ctrl = nullptr;  // [0],[1] carry ping-pong, [2] count-only accumulator
+    unsigned long long *d_ctrl = nullptr;  // [0],[1] carry ping-pong, [2] count-only running total, [3] always 0
     unsigned long long *h_result = nullptr;  // pinned
     void *d_scratch = nullptr;  // ticket, block sums/bases, segment counts, hit masks (see bmx_scanner_scan)
     size_t d_scratch_cap = 0;
@@ -86,6 +86,14 @@ struct bmx_scanner {
     int timing_level = 2;  // 0 none, 1 whole scan, 2 + scan kernel alone
     bmx_stats stats{};
 };
+
+// Device word holding the search's hit count: the carry slot the last scan wrote (positions mode), the
+// running total (count-only mode), or the constant zero while no scan has been launched since begin().
+static const unsigned long long *result_slot(const bmx_scanner *s)
+{
+    if (s->scan_index == 0) return s->d_ctrl + 3;
+    return s->positions ? s->d_ctrl + (s->scan_index & 1u) : s->d_ctrl + 2;
+}
 
 extern "C" {
 
@@ -122,6 +130,7 @@ int bmx_scanner_create(int device, bmx_scanner **out)
     if (!s) return fail(BMX_E_NOMEM, "out of host memory");
     s->device = device;
     cudaError_t e = cudaMalloc(&s->d_ctrl, 64);
+    if (e == cudaSuccess) e = cudaMemset(s->d_ctrl, 0, 64);
     if (e == cudaSuccess) e = cudaHostAlloc(&s->h_result, 64, cudaHostAllocDefault);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_start);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev_stop);
@@ -208,7 +217,8 @@ int bmx_scanner_begin(bmx_scanner *s, int64_t *d_pos_out, int64_t pos_cap, void 
     s->timing_open = false;
     s->stats = bmx_stats{};
     s->stats.variant = s->variant;
-    BMX_CUDA(cudaMemsetAsync(s->d_ctrl, 0, 64, static_cast<cudaStream_t>(stream)));
+    // no device work here: the first scan of the search treats the carried state as zero (ScanArgs::first_scan)
+    (void)stream;
     return BMX_OK;
 }
 
@@ -234,17 +244,17 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     ScanLaunch launch{};
     if (int rc = plan_scan(s->device, s->variant, s->m, s->positions, &a, &launch)) return rc;
 
-    // scratch: [ticket 16 B | block_sum u32 x blocks | seg_count u16 x segs | item_flag u8 x items]  <- zeroed per launch
+    // scratch: [tickets 16 B | scan count u64 + pad | block_sum u32 x blocks | seg_count u16 x segs | item_flag u8 x items]  <- zeroed per launch
     //          [block_base u64 x blocks | mask16 u16 x chunks]                <- written before read
-    const size_t off_bsum = 16;
+    const size_t off_bsum = 32;
     const size_t off_segc = off_bsum + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
     // seg_count is padded to whole blocks: the expand kernel reads a block's 1024 counts with vector loads
     const size_t off_flag = off_segc + (size_t)a.num_blocks * kBlockSegs * 2;
-    const size_t zero_bytes = s->positions ? off_flag + (((size_t)a.num_blocks * kExpandSplit + 15) & ~size_t(15)) : 16;
+    const size_t zero_bytes = s->positions ? off_flag + (((size_t)a.num_blocks * kExpandSplit + 15) & ~size_t(15)) : off_bsum;
     const size_t off_bbase = zero_bytes;
     const size_t off_dense = off_bbase + (((size_t)a.num_blocks * 8 + 15) & ~size_t(15));  // mask16 is read with 16-byte loads
     const size_t off_mask = off_dense + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
-    const size_t scratch = s->positions ? off_mask + (size_t)a.num_segs * kSegChunks * 2 : 16;
+    const size_t scratch = s->positions ? off_mask + (size_t)a.num_segs * kSegChunks * 2 : off_bsum;
     if (scratch > s->d_scratch_cap) {
         BMX_CUDA(cudaStreamSynchronize(st));
         if (s->d_scratch) cudaFree(s->d_scratch);
@@ -265,6 +275,8 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     a.carry_in = s->d_ctrl + (s->scan_index & 1u);
     a.carry_out = s->d_ctrl + ((s->scan_index + 1u) & 1u);
     a.count_acc = s->d_ctrl + 2;
+    a.scan_count = reinterpret_cast<unsigned long long *>(base + 16);
+    a.first_scan = s->scan_index == 0 ? 1u : 0u;
 
     if (s->timing_level >= 1 && !s->timing_open) {
         BMX_CUDA(cudaEventRecord(s->ev_start, st));
@@ -299,7 +311,7 @@ int bmx_scanner_export_result(bmx_scanner *s, void *d_dst, int64_t head, void *s
 {
     if (!s || !d_dst || head < 0) return fail(BMX_E_BADARG, "bmx_scanner_export_result: bad argument");
     BMX_CUDA(cudaSetDevice(s->device));
-    const unsigned long long *src = s->positions ? s->d_ctrl + (s->scan_index & 1u) : s->d_ctrl + 2;
+    const unsigned long long *src = result_slot(s);
     return launch_export_result(src, s->d_pos_out, s->pos_cap, d_dst, s->positions ? head : 0, stream);
 }
 
@@ -308,7 +320,7 @@ int bmx_scanner_finish(bmx_scanner *s, uint64_t *count_out, bmx_stats *stats, vo
     if (!s || !count_out) return fail(BMX_E_BADARG, "bmx_scanner_finish: NULL argument");
     BMX_CUDA(cudaSetDevice(s->device));
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const unsigned long long *src = s->positions ? s->d_ctrl + (s->scan_index & 1u) : s->d_ctrl + 2;
+    const unsigned long long *src = result_slot(s);
     BMX_CUDA(cudaMemcpyAsync(s->h_result, src, sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     BMX_CUDA(cudaStreamSynchronize(st));
     *count_out = (uint64_t)s->h_result[0];
@@ -675,7 +687,7 @@ int bmx_search_partitions(const char *text, const char *pat, const int32_t *se, 
         return rc;
     }
     // the running count lives in the scanner's carry slot after one scan: slot 1
-    if ((rc = launch_partition_count(d_pos, c->scanner->d_ctrl + (c->scanner->scan_index & 1u), max_hits, d_se, d_ans, m,
+    if ((rc = launch_partition_count(d_pos, result_slot(c->scanner), max_hits, d_se, d_ans, m,
                                      nparts, st)) != BMX_OK) {
         cleanup();
         return rc;

@@ -77,7 +77,9 @@ struct ScanArgs {
     int32_t owner_offset;                  // start position of mask bit 0 relative to its chunk (-3 for QGRAM)
     const unsigned long long *carry_in;    // hits reported by earlier chained scans
     unsigned long long *carry_out;         // carry_in + hits of this scan (block-scan kernel)
-    unsigned long long *count_acc;         // count-only mode: atomically accumulated
+    unsigned long long *count_acc;         // count-only mode: running total over the chained scans (last CTA adds scan_count)
+    unsigned long long *scan_count;        // count-only mode: this scan's hits, atomically accumulated; zeroed per launch
+    uint32_t first_scan;                   // first scan of a search: carry_in / count_acc count as 0 (no memset needed)
 };
 
 // Launch description produced by plan_scan() and consumed by launch_scan().

@@ -548,7 +548,14 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     if (!POSITIONS) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) my_count += __shfl_xor_sync(0xFFFFFFFFu, my_count, o);
-        if (lane == 0 && my_count) atomicAdd(A.count_acc, my_count);
+        if (lane == 0 && my_count) atomicAdd(A.scan_count, my_count);
+        // the CTA that finishes last folds this scan's count into the running total of the search
+        __threadfence();
+        bar_sync_consumers();
+        if (tid == 0 && atomicAdd(A.tile_counter + 1, 1u) == gridDim.x - 1) {
+            __threadfence();
+            *A.count_acc = (A.first_scan ? 0ull : *A.count_acc) + __ldcg(A.scan_count);
+        }
         return;
     }
 
@@ -560,52 +567,68 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     bar_sync_consumers();
     if (!ctl->is_last) return;
     __threadfence();
-    // One pass: thread t owns a contiguous run of blocks, sums it (hits and dense blocks), the CTA scans
-    // the 256 partial sums, then every thread writes the bases and the dense list of its run.
-    const uint32_t per = (A.num_blocks + kConsumerThreads - 1) / kConsumerThreads;
-    const uint32_t b0 = min((uint32_t)tid * per, A.num_blocks), b1 = min(b0 + per, A.num_blocks);
-    unsigned long long hits = 0;
-    uint32_t ndense = 0;
-    for (uint32_t b = b0; b < b1; ++b) {
-        const uint32_t v = __ldcg(&A.block_sum[b]);
-        hits += v;
-        ndense += v >= kDenseBlockHits ? 1u : 0u;
-    }
-    unsigned long long hits_incl = hits;
-    uint32_t dense_incl = ndense;
+    // Chunks of 2048 blocks: thread t owns 8 consecutive blocks of the chunk and loads their sums with 8
+    // independent loads (one round trip -- a load-add loop here cost 2 x 8 dependent L2 round trips at the very
+    // end of the kernel), the CTA scans the 256 partial sums, every thread writes its bases and dense blocks.
+    constexpr uint32_t kRun = 8;
+    unsigned long long hits_carry = 0;  // hits / dense blocks in front of the chunk
+    uint32_t dense_carry = 0;
+    for (uint32_t c0 = 0; c0 < A.num_blocks; c0 += kConsumerThreads * kRun) {
+        const uint32_t b0 = c0 + (uint32_t)tid * kRun;
+        uint32_t v[kRun];
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long th = __shfl_up_sync(0xFFFFFFFFu, hits_incl, o);
-        const uint32_t td = __shfl_up_sync(0xFFFFFFFFu, dense_incl, o);
-        if (lane >= o) {
-            hits_incl += th;
-            dense_incl += td;
+        for (uint32_t j = 0; j < kRun; ++j) v[j] = b0 + j < A.num_blocks ? __ldcg(&A.block_sum[b0 + j]) : 0u;
+        unsigned long long hits = 0;
+        uint32_t ndense = 0;
+#pragma unroll
+        for (uint32_t j = 0; j < kRun; ++j) {
+            hits += v[j];
+            ndense += v[j] >= kDenseBlockHits ? 1u : 0u;
         }
-    }
-    if (lane == 31) {
-        ctl->scan_warp[warp] = hits_incl;
-        ctl->scan_dense[warp] = dense_incl;
-    }
-    bar_sync_consumers();
-    unsigned long long hits_before = hits_incl - hits, total_hits = 0;
-    uint32_t dense_before = dense_incl - ndense, total_dense = 0;
-    for (int w = 0; w < kConsumerWarps; ++w) {
-        if (w < warp) {
-            hits_before += ctl->scan_warp[w];
-            dense_before += ctl->scan_dense[w];
+        unsigned long long hits_incl = hits;
+        uint32_t dense_incl = ndense;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long th = __shfl_up_sync(0xFFFFFFFFu, hits_incl, o);
+            const uint32_t td = __shfl_up_sync(0xFFFFFFFFu, dense_incl, o);
+            if (lane >= o) {
+                hits_incl += th;
+                dense_incl += td;
+            }
         }
-        total_hits += ctl->scan_warp[w];
-        total_dense += ctl->scan_dense[w];
-    }
-    for (uint32_t b = b0; b < b1; ++b) {
-        const uint32_t v = __ldcg(&A.block_sum[b]);
-        A.block_base[b] = hits_before;
-        hits_before += v;
-        if (v >= kDenseBlockHits) A.dense_list[dense_before++] = b;  // ascending: expand_kernel walks it in ticket order
+        if (lane == 31) {
+            ctl->scan_warp[warp] = hits_incl;
+            ctl->scan_dense[warp] = dense_incl;
+        }
+        bar_sync_consumers();
+        unsigned long long hits_before = hits_carry + hits_incl - hits, chunk_hits = 0;
+        uint32_t dense_before = dense_carry + dense_incl - ndense, chunk_dense = 0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) {
+            const unsigned long long wh = ctl->scan_warp[w];
+            const uint32_t wd = ctl->scan_dense[w];
+            if (w < warp) {
+                hits_before += wh;
+                dense_before += wd;
+            }
+            chunk_hits += wh;
+            chunk_dense += wd;
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < kRun; ++j) {
+            if (b0 + j < A.num_blocks) {
+                A.block_base[b0 + j] = hits_before;
+                hits_before += v[j];
+                if (v[j] >= kDenseBlockHits) A.dense_list[dense_before++] = b0 + j;  // ascending: expand_kernel walks it in ticket order
+            }
+        }
+        hits_carry += chunk_hits;
+        dense_carry += chunk_dense;
+        bar_sync_consumers();  // scan_warp / scan_dense are rewritten by the next chunk
     }
     if (tid == 0) {
-        *A.carry_out = *A.carry_in + total_hits;
-        A.tile_counter[3] = total_dense;
+        *A.carry_out = (A.first_scan ? 0ull : *A.carry_in) + hits_carry;
+        A.tile_counter[3] = dense_carry;
     }
 }
 
@@ -864,23 +887,34 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
     __shared__ uint16_t s_stage[kExpandWarps][kSegBytes];
     __shared__ uint32_t s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned long long carry = *A.carry_in;
+    const unsigned long long carry = A.first_scan ? 0ull : *A.carry_in;
     const uint32_t dense_items = A.tile_counter[3] * kExpandSplit;  // loaded up front, used by phase 2
 
-    // ---- phase 1: items of sparse blocks, one warp per item, found by one round of flag probes
+    // ---- phase 1: items of sparse blocks, one warp per item.  Lane l of warp g probes unit l * #warps + g,
+    // where a unit is one item flag if a single round of loads then covers the text, else the flags of 4
+    // consecutive items (one 32-bit load: one round covers ~14 GiB with a single resident wave of CTAs).
+    // A sparse text gives every flagged item its own warp, and a dense text spreads evenly.
     {
         const uint32_t gw = blockIdx.x * kExpandWarps + warp, nw = gridDim.x * kExpandWarps;
         const uint32_t items = A.num_blocks * kExpandSplit;
-        for (uint32_t base = 0; base < items; base += nw * 32u) {
+        const bool wide = items > nw * 32u;
+        const uint32_t units = wide ? items / 4u : items, per_block = wide ? kExpandSplit / 4u : kExpandSplit;
+        const uint32_t *flag4 = reinterpret_cast<const uint32_t *>(A.item_flag);
+        for (uint32_t base = 0; base < units; base += nw * 32u) {
             const uint32_t mine = base + (uint32_t)lane * nw + gw;
             // both loads are issued together (no short circuit): one round trip instead of two
-            const uint32_t flag = mine < items ? A.item_flag[mine] : 0u;
-            const uint32_t bsum = mine < items ? A.block_sum[mine / kExpandSplit] : 0u;
-            uint32_t vote = __ballot_sync(0xFFFFFFFFu, (flag != 0) & (bsum < kDenseBlockHits));
-            while (vote) {
-                const int src = __ffs(vote) - 1;
-                vote &= vote - 1;
-                expand_item(A, __shfl_sync(0xFFFFFFFFu, mine, src), carry, s_stage[warp], lane, 1u, 0u);
+            uint32_t flags = mine < units ? (wide ? flag4[mine] : (uint32_t)A.item_flag[mine]) : 0u;
+            const uint32_t bsum = mine < units ? A.block_sum[mine / per_block] : 0u;
+            if (bsum >= kDenseBlockHits) flags = 0u;   // dense blocks belong to phase 2
+#pragma unroll
+            for (uint32_t k = 0; k < 4; ++k) {
+                uint32_t vote = __ballot_sync(0xFFFFFFFFu, ((flags >> (8 * k)) & 0xFFu) != 0u);
+                while (vote) {
+                    const int src = __ffs(vote) - 1;
+                    vote &= vote - 1;
+                    const uint32_t unit = __shfl_sync(0xFFFFFFFFu, mine, src);
+                    expand_item(A, wide ? unit * 4u + k : unit, carry, s_stage[warp], lane, 1u, 0u);
+                }
             }
         }
     }
@@ -1177,8 +1211,13 @@ int launch_emit(const ScanArgs &a, void *stream)
     cudaGetDevice(&dev);
     int &sms = sms_cache[dev & 63];
     if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    // one resident wave of CTAs (a second wave would repeat the whole load-latency chain)
+    static int per_sm = 0;
+    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_kernel, kExpandThreads, 0) != cudaSuccess || per_sm < 1))
+        per_sm = 2;
     const uint32_t items = a.num_blocks * kExpandSplit;
-    const uint32_t grid = std::min<uint32_t>((items + kExpandWarps - 1) / kExpandWarps, (uint32_t)sms * 5u);  // one warp per item
+    uint32_t grid = std::min<uint32_t>((items + kExpandWarps - 1) / kExpandWarps, (uint32_t)(sms * per_sm));
+    grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, (uint32_t)env_int("BMX_EXPAND_GRID", 1 << 30)));  // test knob
     expand_kernel<<<grid, kExpandThreads, 0, st>>>(a);
     e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BMX_E_CUDA, "expand launch: %s", cudaGetErrorString(e));

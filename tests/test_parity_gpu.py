@@ -405,6 +405,28 @@ def test_mid_density_and_mixed_blocks(bmx, oracle, dev):
             assert count == want.size
 
 
+def test_expand_probe_layouts(bmx, oracle, dev, monkeypatch):
+    """The expand kernel probes one item flag per lane when one round of loads covers the text and four
+    flags per lane on multi-GiB texts.  A tiny expand grid (test knob) forces the four-flag layout and many
+    probe rounds on a small text of every density; the result must not change."""
+    rnd = random.Random(4242)
+    n = 6 * (1 << 20) + 12345
+    for sigma, m in [(2, 3), (4, 4), (4, 9), (26, 2), (95, 8)]:
+        text = np.random.default_rng(sigma * 100 + m).integers(97, 97 + sigma, n, dtype=np.uint8).tobytes() if sigma < 95 else \
+            bmx.synth.fill_host(0, n, 5, bmx.synth.ALPHABETS["ascii95"]).tobytes()
+        o = rnd.randint(0, n - m)
+        pat = text[o:o + m]
+        want = oracle.search_np(np.frombuffer(text, dtype=np.uint8), pat, threads=-1)
+        td = to_dev(text, dev, misalign=rnd.randint(0, 17))
+        for grid in ("1", "3", None):
+            if grid is None:
+                monkeypatch.delenv("BMX_EXPAND_GRID", raising=False)
+            else:
+                monkeypatch.setenv("BMX_EXPAND_GRID", grid)
+            count, got, _ = gpu_positions(bmx, td, pat)
+            assert count == want.size and np.array_equal(got, want), (sigma, m, grid)
+
+
 def test_concurrent_host_threads_are_independent(bmx, oracle, dev):
     """The convenience entry points keep per-thread state: searches for different patterns from
     several host threads at once must not disturb each other (the reference is single-threaded;
