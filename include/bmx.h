@@ -53,7 +53,7 @@ typedef enum bmx_variant {
 
 /* Per-call measurements filled by the *_ex / scanner calls (all optional). */
 typedef struct bmx_stats {
-    float device_ms;       /* CUDA-event time of memset + scan kernel(s) on the launching stream */
+    float device_ms;       /* CUDA-event time of the scan + expand kernel(s) on the launching stream */
     int32_t variant;       /* bmx_variant actually run */
     int32_t kernel_launches; /* scan kernels launched by the call */
     int32_t grid;          /* CTAs of the (last) scan kernel */

@@ -76,6 +76,9 @@ struct bmx_scanner {
     unsigned long long *h_result = nullptr;  // pinned
     void *d_scratch = nullptr;  // ticket, block sums/bases, segment counts, hit masks (see bmx_scanner_scan)
     size_t d_scratch_cap = 0;
+    size_t zero_cap = 0;        // bytes of each of the two zero-initialised halves at the front of d_scratch
+    size_t dirty[2] = {0, 0};   // leading bytes of each half that enqueued work leaves non-zero
+    int cur_half = 0;           // half the next scan uses
     int64_t *d_pos_out = nullptr;
     int64_t pos_cap = 0;
     bool positions = false;
@@ -244,50 +247,69 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     ScanLaunch launch{};
     if (int rc = plan_scan(s->device, s->variant, s->m, s->positions, &a, &launch)) return rc;
 
-    // scratch: [tickets 16 B | scan count u64 + pad | block_sum u32 x blocks | seg_count u16 x segs | item_flag u8 x items]  <- zeroed per launch
-    //          [block_base u64 x blocks | mask16 u16 x chunks]                <- written before read
+    // scratch: two "zero halves" [tickets 16 B | scan count u64 + pad | block_sum u32 x blocks | seg_count u16 x segs |
+    //          item_flag u8 x items], each zero whenever a scan starts on it, followed by
+    //          [block_base u64 x blocks | dense_list | mask16 u16 x chunks]                <- written before read.
+    // Scans alternate between the halves: the expand kernel of scan i clears the half scan i-1 used, so in
+    // steady state no memset sits between the kernels; a count-only scan resets its 32-byte header itself.
     const size_t off_bsum = 32;
     const size_t off_segc = off_bsum + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
     // seg_count is padded to whole blocks: the expand kernel reads a block's 1024 counts with vector loads
     const size_t off_flag = off_segc + (size_t)a.num_blocks * kBlockSegs * 2;
     const size_t zero_bytes = s->positions ? off_flag + (((size_t)a.num_blocks * kExpandSplit + 15) & ~size_t(15)) : off_bsum;
-    const size_t off_bbase = zero_bytes;
+    const size_t off_bbase = 0;
     const size_t off_dense = off_bbase + (((size_t)a.num_blocks * 8 + 15) & ~size_t(15));  // mask16 is read with 16-byte loads
     const size_t off_mask = off_dense + (((size_t)a.num_blocks * 4 + 15) & ~size_t(15));
-    const size_t scratch = s->positions ? off_mask + (size_t)a.num_segs * kSegChunks * 2 : off_bsum;
-    if (scratch > s->d_scratch_cap) {
+    const size_t rest_bytes = s->positions ? off_mask + (size_t)a.num_segs * kSegChunks * 2 : 0;
+    if (zero_bytes > s->zero_cap || 2 * s->zero_cap + rest_bytes > s->d_scratch_cap) {
         BMX_CUDA(cudaStreamSynchronize(st));
         if (s->d_scratch) cudaFree(s->d_scratch);
         s->d_scratch = nullptr;
         s->d_scratch_cap = 0;
-        const size_t want = std::max<size_t>(scratch + scratch / 8, 1 << 20);
+        const size_t zcap = std::max<size_t>(s->zero_cap, ((zero_bytes + zero_bytes / 8 + 255) & ~size_t(255)));
+        const size_t want = std::max<size_t>(2 * zcap + rest_bytes + rest_bytes / 8, 1 << 20);
         BMX_CUDA(cudaMalloc(&s->d_scratch, want));
         s->d_scratch_cap = want;
+        s->zero_cap = zcap;
+        BMX_CUDA(cudaMemsetAsync(s->d_scratch, 0, 2 * zcap, st));
+        s->dirty[0] = s->dirty[1] = 0;
+        s->cur_half = 0;
     }
-    unsigned char *base = static_cast<unsigned char *>(s->d_scratch);
+    const int half = s->cur_half;
+    unsigned char *base = static_cast<unsigned char *>(s->d_scratch) + (size_t)half * s->zero_cap;
+    unsigned char *rest = static_cast<unsigned char *>(s->d_scratch) + 2 * s->zero_cap;
+    if (s->dirty[half]) {  // not reached by alternating scans; keeps any other call order correct
+        BMX_CUDA(cudaMemsetAsync(base, 0, s->dirty[half], st));
+        s->dirty[half] = 0;
+    }
     a.tile_counter = reinterpret_cast<uint32_t *>(base);
+    a.scan_count = reinterpret_cast<unsigned long long *>(base + 16);
     a.block_sum = reinterpret_cast<uint32_t *>(base + off_bsum);
     a.seg_count = reinterpret_cast<uint16_t *>(base + off_segc);
     a.item_flag = base + off_flag;
-    a.block_base = reinterpret_cast<unsigned long long *>(base + off_bbase);
-    a.dense_list = reinterpret_cast<uint32_t *>(base + off_dense);
-    a.mask16 = reinterpret_cast<uint16_t *>(base + off_mask);
+    a.block_base = reinterpret_cast<unsigned long long *>(rest + off_bbase);
+    a.dense_list = reinterpret_cast<uint32_t *>(rest + off_dense);
+    a.mask16 = reinterpret_cast<uint16_t *>(rest + off_mask);
+    a.zero_ptr = static_cast<unsigned char *>(s->d_scratch) + (size_t)(1 - half) * s->zero_cap;
+    a.zero_vec16 = s->positions ? (uint32_t)((s->dirty[1 - half] + 15) / 16) : 0u;
     a.carry_in = s->d_ctrl + (s->scan_index & 1u);
     a.carry_out = s->d_ctrl + ((s->scan_index + 1u) & 1u);
     a.count_acc = s->d_ctrl + 2;
-    a.scan_count = reinterpret_cast<unsigned long long *>(base + 16);
     a.first_scan = s->scan_index == 0 ? 1u : 0u;
 
     if (s->timing_level >= 1 && !s->timing_open) {
         BMX_CUDA(cudaEventRecord(s->ev_start, st));
         s->timing_open = true;
     }
-    BMX_CUDA(cudaMemsetAsync(s->d_scratch, 0, zero_bytes, st));
     if (s->timing_level >= 2) BMX_CUDA(cudaEventRecord(s->ev_k0, st));
     if (int rc = launch_scan(a, launch, s->positions, st)) return rc;
     if (s->timing_level >= 2) BMX_CUDA(cudaEventRecord(s->ev_k1, st));
-    if (s->positions)
+    if (s->positions) {
+        s->dirty[half] = zero_bytes;
         if (int rc = launch_emit(a, st)) return rc;
+        s->dirty[1 - half] = 0;   // cleared by the expand kernel just enqueued
+        s->cur_half = 1 - half;
+    }
     if (s->timing_level >= 1) BMX_CUDA(cudaEventRecord(s->ev_stop, st));
 
     s->scan_index += 1;

@@ -65,7 +65,7 @@ struct ScanArgs {
     // output
     int64_t *pos_out;
     int64_t pos_cap;
-    uint32_t *tile_counter;                // [0] tile tickets, [1] CTAs done, [2] dense-item tickets, [3] #dense blocks; zeroed per launch
+    uint32_t *tile_counter;                // [0] tile tickets, [1] CTAs done, [2] dense-item tickets, [3] #dense blocks; zero before the launch
     uint32_t *dense_list;                  // indices of the dense blocks, ascending (written by the last CTA)
     uint16_t *mask16;                      // hit mask per chunk (written only where a segment has hits)
     uint16_t *seg_count;                   // hits per segment, zeroed before the launch
@@ -80,6 +80,8 @@ struct ScanArgs {
     unsigned long long *count_acc;         // count-only mode: running total over the chained scans (last CTA adds scan_count)
     unsigned long long *scan_count;        // count-only mode: this scan's hits, atomically accumulated; zeroed per launch
     uint32_t first_scan;                   // first scan of a search: carry_in / count_acc count as 0 (no memset needed)
+    void *zero_ptr;                        // expand kernel: the OTHER zero-initialised scratch half, left dirty by the scan before
+    uint32_t zero_vec16;                   //   this one; its first zero_vec16 16-byte words are cleared for the next scan (0: nothing)
 };
 
 // Launch description produced by plan_scan() and consumed by launch_scan().

@@ -555,6 +555,10 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         if (tid == 0 && atomicAdd(A.tile_counter + 1, 1u) == gridDim.x - 1) {
             __threadfence();
             *A.count_acc = (A.first_scan ? 0ull : *A.count_acc) + __ldcg(A.scan_count);
+            // leave the header as it was found (all zero): a count-only scan needs no memset before the next one
+            A.tile_counter[0] = 0u;
+            A.tile_counter[1] = 0u;
+            *A.scan_count = 0ull;
         }
         return;
     }
@@ -887,6 +891,11 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
     __shared__ uint16_t s_stage[kExpandWarps][kSegBytes];
     __shared__ uint32_t s_ticket;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // Housekeeping for the NEXT scan: clear the zero-initialised scratch half that the previous scan dirtied
+    // (its expand kernel has finished: stream order).  Fire-and-forget stores under this kernel's load latency,
+    // instead of a memset operation in front of every scan.
+    for (uint32_t i = blockIdx.x * kExpandThreads + threadIdx.x; i < A.zero_vec16; i += gridDim.x * kExpandThreads)
+        static_cast<uint4 *>(A.zero_ptr)[i] = make_uint4(0u, 0u, 0u, 0u);
     const unsigned long long carry = A.first_scan ? 0ull : *A.carry_in;
     const uint32_t dense_items = A.tile_counter[3] * kExpandSplit;  // loaded up front, used by phase 2
 

@@ -310,6 +310,46 @@ def test_scanner_chained_scans_keep_global_order(bmx, oracle, dev):
     assert np.array_equal(out[:count].cpu().numpy(), want)
 
 
+def test_scanner_reuse_across_modes_sizes_and_patterns(bmx, oracle, dev):
+    """One scanner, a long random sequence of searches: count-only and positions, one scan or several chained
+    ones, growing and shrinking texts, changing patterns, searches abandoned without finish().  The scratch the
+    kernels expect to find zeroed is cleaned by the kernels themselves (alternating halves), so every order of
+    calls must leave it clean for the next one."""
+    rnd = random.Random(99)
+    s = bmx.Scanner(0)
+    stream = torch.cuda.current_stream().cuda_stream
+    big = np.random.default_rng(5).integers(97, 101, 9 << 20, dtype=np.uint8)
+    td_big = to_dev(big, dev, misalign=3)
+    out = torch.empty(big.size, dtype=torch.int64, device=dev)
+    for it in range(70):
+        n = rnd.choice([rnd.randint(1, 5000), rnd.randint(5000, 400_000), rnd.randint(400_000, big.size)])
+        off = rnd.randint(0, big.size - n)
+        m = rnd.choice([1, 2, 3, 5, 8, 12, 20])
+        o = rnd.randint(0, big.size - m)
+        pat = big[o:o + m].tobytes()
+        text, td = big[off:off + n], td_big[off:off + n]
+        want = oracle.search_np(text, pat, threads=-1) if n >= m else np.zeros(0, dtype=np.int64)
+        positions = rnd.random() < 0.6
+        s.set_pattern(pat, stream=stream)
+        s.begin(out if positions else None, stream=stream)
+        pieces = rnd.choice([1, 1, 2, 3])
+        cuts = sorted(rnd.randint(0, n) for _ in range(pieces - 1))
+        lo = 0
+        for cut in cuts + [n]:
+            # piece covering the starts [lo, cut - m] needs the bytes [lo, cut); the last piece runs to n
+            hi = cut if cut == n else min(n, cut + m - 1)
+            if hi - lo >= m:
+                s.scan(td[lo:hi], lo, stream=stream)
+            lo = max(lo, cut)
+        if rnd.random() < 0.15:
+            continue                                   # abandoned search: the next begin() starts over
+        count, _ = s.finish(stream=stream)
+        assert count == want.size, (it, n, m, positions, pieces)
+        if positions:
+            assert np.array_equal(out[:count].cpu().numpy(), want), (it, n, m, pieces)
+    s.close()
+
+
 def test_abi_device_entry_point_raw(bmx, oracle, dev):
     """bmx_search_device exactly as a C caller would use it (ctypes, raw pointers)."""
     lib = bmx._lib.load()
