@@ -402,12 +402,43 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t S = A.stages;
 
-    if (tid == 0) {
+    // Fetches one tile (plus the 16 bytes in front of it and the halo behind it) into pipeline slot s.
+    auto fetch_tile = [&](uint32_t tile, uint32_t s) {
+        ctl->slot_tile[s] = (int32_t)tile;
+        uint8_t *dst = stages + (size_t)s * A.stage_stride;
+        const int64_t v0 = (int64_t)tile * TILE;
+        int64_t src_v = v0 - kPre;
+        if (tile == 0) {  // nothing in front of the first tile
+            src_v = 0;
+            dst += kPre;
+        }
+        int64_t end_v = v0 + TILE + (int64_t)A.halo;
+        if (end_v > A.vlen) end_v = A.vlen;
+        const uint32_t bytes = (uint32_t)(end_v - src_v);
+        const uint32_t bulk = bytes & ~15u;
+        // ragged tail of the text (< 16 bytes, last tiles only): plain byte copies
+        for (uint32_t j = bulk; j < bytes; ++j) dst[j] = A.vtext[src_v + j];
+        if (bulk) {
+            mbar_arrive_expect_tx(&ctl->full[s], bulk);
+            tma_bulk_g2s(dst, A.vtext + src_v, bulk, &ctl->full[s]);
+        } else {
+            mbar_arrive(&ctl->full[s]);
+        }
+    };
+
+    // The producer thread sets up the pipeline and has the CTA's first tile -- statically tile blockIdx.x, the
+    // grid never exceeds the tile count -- in flight before anything else happens: the ticket round trip and
+    // the staging of the tables below overlap the first HBM access instead of preceding it.
+    const bool is_producer = tid == kConsumerThreads;
+    uint32_t next_tile = 0;
+    if (is_producer) {
         for (uint32_t s = 0; s < S; ++s) {
             mbar_init(&ctl->full[s], 1);
             mbar_init(&ctl->empty[s], kConsumerWarps);
         }
         mbar_fence_init();
+        fetch_tile(blockIdx.x, 0);
+        next_tile = gridDim.x + atomicAdd(A.tile_counter, 1u);  // tickets hand out the tiles behind the static ones
     }
     if (A.pat_smem) {
         for (int i = tid; i < 256; i += kThreads) ctl->bad[i] = A.g_bad[i];
@@ -428,38 +459,18 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     // ------------------------------------------------------------------ producer warp
     if (warp == kConsumerWarps) {
         if (lane != 0) return;
-        uint32_t next_tile = atomicAdd(A.tile_counter, 1u);
-        for (uint32_t it = 0;; ++it) {
+        for (uint32_t it = 1;; ++it) {
             const uint32_t s = it % S;
             const uint32_t tile = next_tile;
             const bool live = tile < A.num_tiles;
-            if (live) next_tile = atomicAdd(A.tile_counter, 1u);  // ticket for the next round, in flight during the wait
+            if (live) next_tile = gridDim.x + atomicAdd(A.tile_counter, 1u);  // ticket for the next round, in flight during the wait
             mbar_wait(&ctl->empty[s], ((it / S) & 1u) ^ 1u);
             if (!live) {
                 ctl->slot_tile[s] = -1;
                 mbar_arrive(&ctl->full[s]);
                 break;
             }
-            ctl->slot_tile[s] = (int32_t)tile;
-            uint8_t *dst = stages + (size_t)s * A.stage_stride;
-            const int64_t v0 = (int64_t)tile * TILE;
-            int64_t src_v = v0 - kPre;
-            if (tile == 0) {  // nothing in front of the first tile
-                src_v = 0;
-                dst += kPre;
-            }
-            int64_t end_v = v0 + TILE + (int64_t)A.halo;
-            if (end_v > A.vlen) end_v = A.vlen;
-            const uint32_t bytes = (uint32_t)(end_v - src_v);
-            const uint32_t bulk = bytes & ~15u;
-            // ragged tail of the text (< 16 bytes, last tiles only): plain byte copies
-            for (uint32_t j = bulk; j < bytes; ++j) dst[j] = A.vtext[src_v + j];
-            if (bulk) {
-                mbar_arrive_expect_tx(&ctl->full[s], bulk);
-                tma_bulk_g2s(dst, A.vtext + src_v, bulk, &ctl->full[s]);
-            } else {
-                mbar_arrive(&ctl->full[s]);
-            }
+            fetch_tile(tile, s);
         }
         return;
     }
