@@ -57,7 +57,6 @@ struct ScanArgs {
     uint32_t hmul;          // QGRAM: hash multiplier K << (32 - 8*(q-4)); the shift drops the bytes beyond the q-gram
     uint32_t hmulr[4];      // QGRAM, 7 <= m <= 10: one multiplier per residue (residue r sees min(8, m - r) bytes)
     uint32_t mulc;          // WINDOW: 2^(32-8q), drops the bytes beyond q
-    uint32_t shl[3];        // WINDOW: 2^24, 2^16, 2^8 (funnel shifts done as multiplies on the FMA pipe)
     // per-pattern block in global memory
     const uint8_t *g_pat;
     const int32_t *g_bad;

@@ -196,8 +196,7 @@ enum : int { kQgram = 1, kWindow = 2, kShiftAnd = 3 };
 
 // WINDOW: the 4-byte window that starts s bytes into `lo` (continuing in `hi`).  (Building the
 // shifted windows on the FMA pipe with IMAD.HI/IMAD instead of SHF was measured 13 % slower.)
-template <bool Q4>
-__device__ __forceinline__ uint32_t window_at(uint32_t lo, uint32_t hi, int s, const ScanArgs &)
+__device__ __forceinline__ uint32_t window_at(uint32_t lo, uint32_t hi, int s)
 {
     return s == 0 ? lo : __funnelshift_r(lo, hi, 8 * s);
 }
@@ -241,7 +240,7 @@ __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const Sc
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
             for (int sh = 0; sh < 4; ++sh) {
-                const uint32_t x = window_at<FLAG>(ww[j], ww[j + 1], sh, A);
+                const uint32_t x = window_at(ww[j], ww[j + 1], sh);
                 any |= FLAG ? (x == tg) : (x * mc == tg);
             }
         }
@@ -270,7 +269,7 @@ __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, con
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
             for (int sh = 0; sh < 4; ++sh) {
-                const uint32_t x = window_at<FLAG>(ww[j], ww[j + 1], sh, A);
+                const uint32_t x = window_at(ww[j], ww[j + 1], sh);
                 mask |= (uint32_t)(FLAG ? (x == A.f[0]) : (x * A.mulc == A.f[0])) << (4 * j + sh);
             }
         }
@@ -1065,9 +1064,6 @@ void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, Sca
     a->f[0] = a->f[1] = a->f[2] = a->f[3] = 0;
     a->hmul = kHashMul;
     a->mulc = 1u;
-    a->shl[0] = 1u << 24;   // multiplier that shifts a word right by 8 (high half) / left by 24 (low half)
-    a->shl[1] = 1u << 16;
-    a->shl[2] = 1u << 8;
     if (variant == BMX_VARIANT_QGRAM) {
         // residue r (pattern byte r on a word boundary) can use min(8, m - r) pattern bytes; for m >= 11
         // that is 8 for every residue and one multiplier serves all four (a->hmul, the FULL8 kernels)
