@@ -112,6 +112,20 @@ int bmx_search_device(const void *d_text, int64_t n, const char *pat, int32_t m,
                       int64_t *d_pos_out, int64_t pos_cap, uint64_t *count_out,
                       float *device_ms, void *stream);
 
+/*
+ * First occurrence with early exit -- the query of the vendored CUDA sample
+ * CUDA/Parallel-Programs-master/cuda/boyer-moore/boyer-moore.cu:62-86 (which leaves the index of SOME
+ * occurrence in d_retval, -1 if none), made well defined: *first_out = the SMALLEST start position p with
+ * text[p..p+m) == pattern, or -1.  Equal to the first entry of bmx_search's list.  The text is scanned in
+ * order in growing chunks and scanning (for host text: also the host->device copies) stops after the first
+ * chunk that holds a match, so an early match costs microseconds, not a pass over the text.
+ * bmx_find_first: host text (pinned or pageable).  bmx_find_first_device: d_text is a DEVICE pointer,
+ * work is launched on `stream` and waited for.
+ */
+int bmx_find_first(const char *text, int64_t n, const char *pat, int32_t m, int64_t *first_out);
+int bmx_find_first_device(const void *d_text, int64_t n, const char *pat, int32_t m, int64_t *first_out,
+                          void *stream);
+
 /* As bmx_search_device with: pos_base added to every reported position (multi-GPU shards report
  * global offsets), explicit variant, full measurements. */
 int bmx_search_device_ex(const void *d_text, int64_t n, const char *pat, int32_t m,

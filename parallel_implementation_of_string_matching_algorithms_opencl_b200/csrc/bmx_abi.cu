@@ -430,6 +430,16 @@ void parallel_copy(void *dst, const void *src, size_t bytes, int threads)
     for (auto &h : helpers) h.join();
 }
 
+// First chunk of a find-first search (doubles up to 1 GiB); BMX_FIND_CHUNK_KB is a test knob.
+int64_t find_first_chunk_bytes()
+{
+    if (const char *e = getenv("BMX_FIND_CHUNK_KB")) {
+        const long kb = atol(e);
+        if (kb > 0) return (int64_t)kb << 10;
+    }
+    return (int64_t)16 << 20;
+}
+
 bool is_pinned_host(const void *p)
 {
     cudaPointerAttributes attr;
@@ -471,6 +481,61 @@ int bmx_search_device(const void *d_text, int64_t n, const char *pat, int32_t m,
     return rc;
 }
 
+
+// First occurrence with early exit.  The text is scanned as chained scans of growing chunks (16 MiB doubling
+// to 1 GiB; starts [s_k, e_k) need the bytes [s_k, e_k + m - 1)) with room for ONE position: chunks run in
+// text order and a truncated list keeps the smallest positions, so that slot ends up holding the first
+// occurrence.  After every chunk {count, first} is exported and copied to pinned memory; the host reads the
+// result of chunk k-1 while chunk k is already running, so the GPU never waits for the host and at most one
+// chunk is scanned in vain.
+int bmx_find_first_device(const void *d_text, int64_t n, const char *pat, int32_t m, int64_t *first_out, void *stream)
+{
+    if (!first_out || !pat) return fail(BMX_E_BADARG, "bmx_find_first_device: pat/first_out must be non-NULL");
+    if (n < 0 || (!d_text && n > 0)) return fail(BMX_E_BADARG, "bmx_find_first_device: bad text (n=%lld)", (long long)n);
+    *first_out = -1;
+    int device = 0;
+    if (int rc = check_device(0)) return rc;
+    BMX_CUDA(cudaGetDevice(&device));
+    ThreadCtx *c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    bmx_scanner *s = c->scanner;
+    if (int rc = bmx_scanner_set_pattern(s, pat, m, BMX_VARIANT_AUTO, stream)) return rc;
+    if (n < m) return BMX_OK;
+    if (int rc = ensure_streams(*c, device, 2)) return rc;
+    int64_t *d_slot = reinterpret_cast<int64_t *>(s->d_ctrl + 4);  // [4] first position, [5..7] exported {count, held, first}
+    if (int rc = bmx_scanner_begin(s, d_slot, 1, stream)) return rc;
+
+    int64_t chunk = find_first_chunk_bytes();
+    const unsigned char *text = static_cast<const unsigned char *>(d_text);
+    const int64_t last_start = n - m;
+    int64_t k = 0;
+    bool found = false;
+    auto result_of = [&](int64_t kk) -> bool {   // waits for chunk kk's exported result
+        if (cudaEventSynchronize(c->events[(size_t)(kk & 1)]) != cudaSuccess) return false;
+        const unsigned long long *h = s->h_result + 3 * (kk & 1);
+        if (h[0] == 0) return false;
+        *first_out = (int64_t)h[2];
+        return true;
+    };
+    for (int64_t s0 = 0; s0 <= last_start; ++k) {
+        const int64_t e0 = std::min(last_start + 1, s0 + chunk);
+        if (int rc = bmx_scanner_scan(s, text + s0, e0 - s0 + m - 1, s0, stream)) return rc;
+        if (int rc = bmx_scanner_export_result(s, d_slot + 1, 1, stream)) return rc;
+        BMX_CUDA(cudaMemcpyAsync(s->h_result + 3 * (k & 1), d_slot + 1, 24, cudaMemcpyDeviceToHost, st));
+        BMX_CUDA(cudaEventRecord(c->events[(size_t)(k & 1)], st));
+        if (k >= 1 && result_of(k - 1)) {
+            found = true;
+            break;
+        }
+        s0 = e0;
+        chunk = std::min<int64_t>(chunk * 2, (int64_t)1 << 30);
+    }
+    BMX_CUDA(cudaStreamSynchronize(st));  // the scanner and its scratch are idle again when this returns
+    if (!found && k >= 1) result_of(k - 1);
+    return BMX_OK;
+}
+
 }  // extern "C"
 
 namespace {
@@ -478,8 +543,12 @@ namespace {
 // Host text -> device (chunked, overlapped with scanning) -> hits in a device buffer.  On success *d_pos_out
 // (when want_pos) is a stream-ordered allocation on c.scan_stream holding min(count, dev_cap) global
 // positions (start + pos_base); the caller copies it out and frees it with cudaFreeAsync(.., c.scan_stream).
+// With first_out (find-first mode: want_pos, dev_cap = 1) the result of every chunk is read back one chunk
+// behind the scans, and both the copies and the scans stop after the first chunk that holds a match;
+// *first_out is that match's position (or stays -1) and *count_out is then only the count so far.
 int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, const char *pat, int32_t m, int64_t pos_base,
-                    bool want_pos, int64_t dev_cap, int32_t variant, int64_t **d_pos_out, uint64_t *count_out, bmx_stats *stats)
+                    bool want_pos, int64_t dev_cap, int32_t variant, int64_t **d_pos_out, uint64_t *count_out, bmx_stats *stats,
+                    int64_t *first_out = nullptr)
 {
     ThreadCtx *c = &ctx;
     *count_out = 0;
@@ -495,7 +564,8 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
     }
     chunk = std::max<int64_t>(chunk, (int64_t)m * 2);
     const int64_t nchunks = (n + chunk - 1) / chunk;
-    if (int rc = ensure_streams(*c, device, (size_t)nchunks + kBounce + 1)) return rc;
+    if (int rc = ensure_streams(*c, device, (size_t)nchunks + kBounce + 3)) return rc;
+    const size_t ev_first = (size_t)nchunks + kBounce + 1;  // two events: "result of scan q exported" (find-first mode)
 
     if (!want_pos) dev_cap = 0;
     unsigned char *d_text = nullptr;
@@ -544,7 +614,16 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
     }
 
     int64_t scanned = 0;  // start positions < scanned are done
-    for (int64_t k = 0; k < nchunks; ++k) {
+    int64_t q = 0;        // find-first mode: scans enqueued so far
+    bool found = false;
+    auto first_of = [&](int64_t qq) -> bool {   // waits for scan qq's exported {count, held, first position}
+        if (cudaEventSynchronize(c->events[ev_first + (size_t)(qq & 1)]) != cudaSuccess) return false;
+        const unsigned long long *h = c->scanner->h_result + 3 * (qq & 1);
+        if (h[0] == 0) return false;
+        *first_out = (int64_t)h[2];
+        return true;
+    };
+    for (int64_t k = 0; k < nchunks && !found; ++k) {
         const int64_t off = k * chunk;
         const int64_t len = std::min(chunk, n - off);
         const char *src = text + off;
@@ -570,6 +649,17 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
                 return rc;
             }
             scanned = have - m + 1;
+            if (first_out) {
+                int64_t *d_slot = reinterpret_cast<int64_t *>(c->scanner->d_ctrl + 5);
+                if ((rc = bmx_scanner_export_result(c->scanner, d_slot, 1, c->scan_stream)) != BMX_OK) {
+                    cleanup();
+                    return rc;
+                }
+                BMX_TRY(cudaMemcpyAsync(c->scanner->h_result + 3 * (q & 1), d_slot, 24, cudaMemcpyDeviceToHost, c->scan_stream));
+                BMX_TRY(cudaEventRecord(c->events[ev_first + (size_t)(q & 1)], c->scan_stream));
+                if (q >= 1) found = first_of(q - 1);
+                ++q;
+            }
         }
     }
     uint64_t count = 0;
@@ -580,6 +670,7 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
     }
     *count_out = count;
     if (stats) *stats = st;
+    if (first_out && !found && q >= 1) first_of(q - 1);
     BMX_TRY(cudaFreeAsync(d_text, c->scan_stream));
     d_text = nullptr;
     if (d_pos_out) {
@@ -630,6 +721,30 @@ int bmx_search(const char *text, int64_t n, const char *pat, int32_t m, int64_t 
     if (int rc = check_device(0)) return rc;
     BMX_CUDA(cudaGetDevice(&device));
     return bmx_search_ex(device, text, n, pat, m, pos_out, pos_cap, count_out, BMX_VARIANT_AUTO, nullptr);
+}
+
+int bmx_find_first(const char *text, int64_t n, const char *pat, int32_t m, int64_t *first_out)
+{
+    if (!first_out || !pat) return fail(BMX_E_BADARG, "bmx_find_first: pat/first_out must be non-NULL");
+    if (n < 0 || (!text && n > 0)) return fail(BMX_E_BADARG, "bmx_find_first: bad text (n=%lld)", (long long)n);
+    if (m <= 0 || m > BMX_MAX_PATTERN)
+        return fail(BMX_E_BADARG, "pattern length %d outside 1..%d (an empty pattern is rejected)", m, BMX_MAX_PATTERN);
+    *first_out = -1;
+    int device = 0;
+    if (int rc = check_device(0)) return rc;
+    BMX_CUDA(cudaGetDevice(&device));
+    ThreadCtx *c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    if (n < m) return BMX_OK;
+    int64_t *d_pos = nullptr;
+    uint64_t count = 0;
+    if (int rc = ingest_and_scan(*c, device, text, n, pat, m, 0, true, 1, BMX_VARIANT_AUTO, &d_pos, &count, nullptr, first_out)) return rc;
+    if (d_pos) cudaFreeAsync(d_pos, c->scan_stream);
+    // copies of chunks behind the match may still be in flight: the caller's buffer must be free on return
+    cudaError_t e = cudaStreamSynchronize(c->copy_stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->scan_stream);
+    if (e != cudaSuccess) return fail(BMX_E_CUDA, "bmx_find_first: %s", cudaGetErrorString(e));
+    return BMX_OK;
 }
 
 int bmx_search_partitions(const char *text, const char *pat, const int32_t *se, int32_t *ans, const int32_t *gs,

@@ -141,6 +141,36 @@ def search_device(text, pattern, pos_out=None, max_positions: int | None = None,
     return count.value, found, stats.as_dict()
 
 
+def find_first(text, pattern) -> int:
+    """Smallest start position of pattern in HOST text, or -1 -- the early-exit "first occurrence" query of
+    the vendored CUDA sample (CUDA/Parallel-Programs-master/cuda/boyer-moore/boyer-moore.cu:62-86), equal to
+    search()'s first position.  Copies and scans stop after the first chunk that holds a match."""
+    lib = _lib.load()
+    pat = _as_bytes(pattern)
+    ptr, n, keep = _host_text(text)
+    first = c_int64(-1)
+    check(lib.bmx_find_first(ptr, n, pat, len(pat), ctypes.byref(first)))
+    del keep
+    return first.value
+
+
+def find_first_device(text, pattern, stream=None) -> int:
+    """find_first() for a contiguous CUDA uint8 tensor (growing chunks, at most one chunk scanned in vain)."""
+    import torch
+
+    lib = _lib.load()
+    pat = _as_bytes(pattern)
+    if not text.is_cuda or text.dtype != torch.uint8 or not text.is_contiguous():
+        raise TypeError("find_first_device() needs a contiguous CUDA uint8 tensor")
+    n = text.numel()
+    first = c_int64(-1)
+    with torch.cuda.device(text.device):
+        s = stream if stream is not None else torch.cuda.current_stream(text.device)
+        check(lib.bmx_find_first_device(c_void_p(text.data_ptr() if n else 0), n, pat, len(pat), ctypes.byref(first),
+                                        c_void_p(s.cuda_stream)))
+    return first.value
+
+
 def search_partitions(text, pattern, se, gs=None, bs=None) -> np.ndarray:
     """Mirror of the kernel entry `search` (kernel1.cl:1): per-range counts ans[nparts]."""
     lib = _lib.load()

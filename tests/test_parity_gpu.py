@@ -350,6 +350,48 @@ def test_scanner_reuse_across_modes_sizes_and_patterns(bmx, oracle, dev):
     s.close()
 
 
+def test_find_first_equals_first_position_of_the_serial_result(bmx, oracle, dev, monkeypatch):
+    """bmx_find_first / bmx_find_first_device: the smallest start position, -1 without a
+    match -- checked against the oracle's list and bytes.find, with matches in the first chunk, in later
+    chunks, straddling chunk seams, at 0 and at n-m, and tiny chunks (test knob) that force many rounds."""
+    rnd = random.Random(2024)
+    for it in range(60):
+        sigma = rnd.choice([2, 4, 26, 200])
+        n = rnd.choice([rnd.randint(1, 300), rnd.randint(300, 300_000)])
+        m = rnd.choice([1, 2, 3, 5, 8, 16, 33])
+        text = bytearray(rnd.randrange(30, 30 + sigma) for _ in range(n))
+        pat = bytes(rnd.randrange(30, 30 + sigma) for _ in range(m))
+        mode = rnd.choice(["random", "late", "end", "start", "none"])
+        if n >= m and mode != "none":
+            at = {"random": rnd.randint(0, n - m), "late": max(0, n - m - rnd.randint(0, 50)), "end": n - m, "start": 0}[mode]
+            text[at:at + m] = pat
+        text = bytes(text)
+        want_list = oracle.search(text, pat)
+        want = int(want_list[0]) if want_list.size else -1
+        assert want == text.find(pat)
+        for kb in ("1", "7", None):
+            if kb is None:
+                monkeypatch.delenv("BMX_FIND_CHUNK_KB", raising=False)
+                monkeypatch.delenv("BMX_H2D_CHUNK_MB", raising=False)
+            else:
+                monkeypatch.setenv("BMX_FIND_CHUNK_KB", kb)
+            td = to_dev(text, dev, misalign=rnd.randint(0, 17))
+            assert bmx.find_first_device(td, pat) == want, (it, n, m, mode, kb, "device")
+            assert bmx.find_first(text, pat) == want, (it, n, m, mode, kb, "host")
+    # host flavour across several H2D chunks (1 MiB chunks): match only in the last chunk, then none at all
+    monkeypatch.setenv("BMX_H2D_CHUNK_MB", "1")
+    big = bmx.synth.fill_host(0, 5 * (1 << 20) + 77, 9, bmx.synth.ALPHABETS["ascii95"])
+    pat = b"\x01needle\x02"
+    assert bmx.find_first(big, pat) == -1
+    for at in (0, (1 << 20) - 4, 3 * (1 << 20) + 5, big.size - len(pat)):
+        t = big.copy()
+        t[at:at + len(pat)] = np.frombuffer(pat, dtype=np.uint8)
+        assert bmx.find_first(t, pat) == at
+        assert bmx.find_first_device(to_dev(t, dev), pat) == at
+    with pytest.raises(bmx.BmxError):
+        bmx.find_first(b"abc", b"")
+
+
 def test_abi_device_entry_point_raw(bmx, oracle, dev):
     """bmx_search_device exactly as a C caller would use it (ctypes, raw pointers)."""
     lib = bmx._lib.load()
