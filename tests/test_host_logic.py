@@ -120,6 +120,9 @@ def test_no_cpu_fallback(bmx):
     # m > n is still answered without a device only after the device check: no silent CPU path
     with pytest.raises(bmx.BmxError):
         bmx.search(b"ab", b"abc")
+    with pytest.raises(bmx.BmxError) as e:
+        bmx.find_first(b"hello world", b"o")
+    assert e.value.code == bmx._lib.BMX_E_NODEVICE
 
 
 def test_product_sources_never_touch_the_oracle():
