@@ -113,6 +113,16 @@ int bmx_search_device(const void *d_text, int64_t n, const char *pat, int32_t m,
                       float *device_ms, void *stream);
 
 /*
+ * K patterns over one host text (multi-pattern batching; the reference builds its tables once per
+ * pattern, BoyreMoore.cpp:150-190, and would re-send the text for each).  The text is copied to the device
+ * ONCE, overlapped with the scan for pats[0]; every further pattern scans the resident copy.  Per pattern k:
+ * counts[k] and, when pos_out && pos_out[k], the first min(counts[k], pos_cap[k]) ascending positions --
+ * exactly what bmx_search_ex returns for that pattern alone.  A pattern longer than the text counts 0.
+ */
+int bmx_search_multi(int device, const char *text, int64_t n, int32_t npat, const char *const *pats,
+                     const int32_t *ms, int64_t *const *pos_out, const int64_t *pos_cap, uint64_t *counts);
+
+/*
  * First occurrence with early exit -- the query of the vendored CUDA sample
  * CUDA/Parallel-Programs-master/cuda/boyer-moore/boyer-moore.cu:62-86 (which leaves the index of SOME
  * occurrence in d_retval, -1 if none), made well defined: *first_out = the SMALLEST start position p with

@@ -27,7 +27,7 @@ VARIANT_NAMES = {0: "auto", 1: "qgram", 2: "window", 3: "shiftand"}
 EXPORTS = [
     "bmx_version", "bmx_last_error", "bmx_device_count", "bmx_build_tables", "bmx_search",
     "bmx_search_ex", "bmx_search_device", "bmx_search_device_ex", "bmx_search_partitions",
-    "bmx_find_first", "bmx_find_first_device",
+    "bmx_find_first", "bmx_find_first_device", "bmx_search_multi",
     "bmx_scanner_create", "bmx_scanner_destroy", "bmx_scanner_set_pattern", "bmx_scanner_begin",
     "bmx_scanner_scan", "bmx_scanner_finish", "bmx_scanner_export_result", "bmx_scanner_set_timing", "bmx_mg_create", "bmx_mg_destroy", "bmx_mg_device_count", "bmx_mg_search", "bmx_synth_fill_device", "bmx_partition_words",
 ]
@@ -84,6 +84,8 @@ def load() -> ctypes.CDLL:
                                       POINTER(c_uint64), POINTER(c_float), c_void_p]
     lib.bmx_search_device_ex.argtypes = [c_void_p, c_int64, c_char_p, c_int32, c_int64, c_void_p, c_int64,
                                          POINTER(c_uint64), c_int32, POINTER(BmxStats), c_void_p]
+    lib.bmx_search_multi.argtypes = [c_int, c_void_p, c_int64, c_int32, POINTER(c_char_p), POINTER(c_int32),
+                                     POINTER(c_void_p), POINTER(c_int64), POINTER(c_uint64)]
     lib.bmx_find_first.argtypes = [c_void_p, c_int64, c_char_p, c_int32, POINTER(c_int64)]
     lib.bmx_find_first_device.argtypes = [c_void_p, c_int64, c_char_p, c_int32, POINTER(c_int64), c_void_p]
     lib.bmx_search_partitions.argtypes = [c_void_p, c_char_p, POINTER(c_int32), POINTER(c_int32),

@@ -543,18 +543,21 @@ namespace {
 // Host text -> device (chunked, overlapped with scanning) -> hits in a device buffer.  On success *d_pos_out
 // (when want_pos) is a stream-ordered allocation on c.scan_stream holding min(count, dev_cap) global
 // positions (start + pos_base); the caller copies it out and frees it with cudaFreeAsync(.., c.scan_stream).
+// With keep_text the device copy of the text (a stream-ordered allocation on c.scan_stream, n + 16 bytes) is
+// handed to the caller instead of being freed, and the text is ingested even when it is shorter than the pattern.
 // With first_out (find-first mode: want_pos, dev_cap = 1) the result of every chunk is read back one chunk
 // behind the scans, and both the copies and the scans stop after the first chunk that holds a match;
 // *first_out is that match's position (or stays -1) and *count_out is then only the count so far.
 int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, const char *pat, int32_t m, int64_t pos_base,
                     bool want_pos, int64_t dev_cap, int32_t variant, int64_t **d_pos_out, uint64_t *count_out, bmx_stats *stats,
-                    int64_t *first_out = nullptr)
+                    int64_t *first_out = nullptr, unsigned char **keep_text = nullptr)
 {
     ThreadCtx *c = &ctx;
     *count_out = 0;
     if (d_pos_out) *d_pos_out = nullptr;
     if (stats) *stats = bmx_stats{};
-    if (n < m) return BMX_OK;
+    if (keep_text) *keep_text = nullptr;
+    if (n < m && !(keep_text && n > 0)) return BMX_OK;
     BMX_CUDA(cudaSetDevice(device));
 
     int64_t chunk = (int64_t)64 << 20;
@@ -671,7 +674,11 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
     *count_out = count;
     if (stats) *stats = st;
     if (first_out && !found && q >= 1) first_of(q - 1);
-    BMX_TRY(cudaFreeAsync(d_text, c->scan_stream));
+    if (keep_text) {
+        *keep_text = d_text;
+    } else {
+        BMX_TRY(cudaFreeAsync(d_text, c->scan_stream));
+    }
     d_text = nullptr;
     if (d_pos_out) {
         *d_pos_out = d_pos;
@@ -721,6 +728,56 @@ int bmx_search(const char *text, int64_t n, const char *pat, int32_t m, int64_t 
     if (int rc = check_device(0)) return rc;
     BMX_CUDA(cudaGetDevice(&device));
     return bmx_search_ex(device, text, n, pat, m, pos_out, pos_cap, count_out, BMX_VARIANT_AUTO, nullptr);
+}
+
+// K patterns over one host text: the text crosses PCIe ONCE (chunked, overlapped with the scan for the first
+// pattern); the other patterns are scans of the resident copy, microseconds per GiB next to the ingest.
+int bmx_search_multi(int device, const char *text, int64_t n, int32_t npat, const char *const *pats, const int32_t *ms,
+                     int64_t *const *pos_out, const int64_t *pos_cap, uint64_t *counts)
+{
+    if (npat < 0 || (npat > 0 && (!pats || !ms || !counts))) return fail(BMX_E_BADARG, "bmx_search_multi: NULL argument or npat < 0");
+    if (n < 0 || (!text && n > 0)) return fail(BMX_E_BADARG, "bmx_search_multi: bad text (n=%lld)", (long long)n);
+    for (int32_t k = 0; k < npat; ++k) {
+        if (!pats[k] || ms[k] <= 0 || ms[k] > BMX_MAX_PATTERN)
+            return fail(BMX_E_BADARG, "pattern %d: length %d outside 1..%d or NULL (an empty pattern is rejected)", k, ms[k], BMX_MAX_PATTERN);
+        if (pos_out && pos_out[k] && (!pos_cap || pos_cap[k] < 0)) return fail(BMX_E_BADARG, "pattern %d: pos_cap < 0 or missing", k);
+        counts[k] = 0;
+    }
+    ThreadCtx *c = nullptr;
+    if (int rc = get_ctx(device, &c)) return rc;
+    if (npat == 0 || n == 0) return BMX_OK;
+    auto cap_of = [&](int32_t k) -> int64_t {
+        if (!pos_out || !pos_out[k] || n < ms[k]) return 0;
+        return std::min(pos_cap[k], n - ms[k] + 1);
+    };
+    unsigned char *d_text = nullptr;
+    int rc = BMX_OK;
+    for (int32_t k = 0; k < npat && rc == BMX_OK; ++k) {
+        const int64_t dev_cap = cap_of(k);
+        int64_t *d_pos = nullptr;
+        if (k == 0) {
+            rc = ingest_and_scan(*c, device, text, n, pats[0], ms[0], 0, dev_cap > 0, dev_cap, BMX_VARIANT_AUTO, &d_pos, &counts[0],
+                                 nullptr, nullptr, &d_text);
+        } else if (n >= ms[k]) {
+            cudaError_t e = dev_cap > 0 ? cudaMallocAsync(reinterpret_cast<void **>(&d_pos), (size_t)dev_cap * 8, c->scan_stream) : cudaSuccess;
+            if (e != cudaSuccess) {
+                rc = fail(e == cudaErrorMemoryAllocation ? BMX_E_NOMEM : BMX_E_CUDA, "bmx_search_multi: %s", cudaGetErrorString(e));
+                break;
+            }
+            if ((rc = bmx_scanner_set_pattern(c->scanner, pats[k], ms[k], BMX_VARIANT_AUTO, c->scan_stream)) == BMX_OK &&
+                (rc = bmx_scanner_begin(c->scanner, d_pos, dev_cap, c->scan_stream)) == BMX_OK &&
+                (rc = bmx_scanner_scan(c->scanner, d_text, n, 0, c->scan_stream)) == BMX_OK)
+                rc = bmx_scanner_finish(c->scanner, &counts[k], nullptr, c->scan_stream);
+        }
+        const int64_t ncopy = rc == BMX_OK ? std::min<int64_t>((int64_t)counts[k], dev_cap) : 0;
+        if (ncopy > 0 && cudaMemcpyAsync(pos_out[k], d_pos, (size_t)ncopy * 8, cudaMemcpyDeviceToHost, c->scan_stream) != cudaSuccess)
+            rc = fail(BMX_E_CUDA, "bmx_search_multi: position read-back failed");
+        if (d_pos) cudaFreeAsync(d_pos, c->scan_stream);
+    }
+    if (d_text) cudaFreeAsync(d_text, c->scan_stream);
+    const cudaError_t e = cudaStreamSynchronize(c->scan_stream);
+    if (rc == BMX_OK && e != cudaSuccess) rc = fail(BMX_E_CUDA, "bmx_search_multi: %s", cudaGetErrorString(e));
+    return rc;
 }
 
 int bmx_find_first(const char *text, int64_t n, const char *pat, int32_t m, int64_t *first_out)

@@ -141,6 +141,28 @@ def search_device(text, pattern, pos_out=None, max_positions: int | None = None,
     return count.value, found, stats.as_dict()
 
 
+def search_multi(text, patterns, max_positions: int | None = None, device: int | None = None):
+    """K patterns over one HOST text with a single host->device copy (multi-pattern batching).
+    Returns [(count, positions[int64])] in pattern order, each equal to search(text, pattern)."""
+    lib = _lib.load()
+    pats = [_as_bytes(p) for p in patterns]
+    ptr, n, keep = _host_text(text)
+    k = len(pats)
+    caps = [max(n - len(p) + 1, 0) if max_positions is None else int(max_positions) for p in pats]
+    bufs = [np.empty(cap, dtype=np.int64) for cap in caps]
+    c_pats = (ctypes.c_char_p * k)(*pats)
+    c_ms = (c_int32 * k)(*[len(p) for p in pats])
+    c_pos = (c_void_p * k)(*[b.ctypes.data if b.size else None for b in bufs])
+    c_caps = (c_int64 * k)(*caps)
+    counts = (c_uint64 * k)()
+    if device is None:
+        import torch
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    check(lib.bmx_search_multi(device, ptr, n, k, c_pats, c_ms, c_pos, c_caps, counts))
+    del keep
+    return [(int(counts[i]), bufs[i][: min(int(counts[i]), caps[i])]) for i in range(k)]
+
+
 def find_first(text, pattern) -> int:
     """Smallest start position of pattern in HOST text, or -1 -- the early-exit "first occurrence" query of
     the vendored CUDA sample (CUDA/Parallel-Programs-master/cuda/boyer-moore/boyer-moore.cu:62-86), equal to

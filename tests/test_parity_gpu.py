@@ -392,6 +392,39 @@ def test_find_first_equals_first_position_of_the_serial_result(bmx, oracle, dev,
         bmx.find_first(b"abc", b"")
 
 
+def test_search_multi_shares_one_ingest(bmx, oracle, monkeypatch):
+    """bmx_search_multi (first cut): K patterns, one host->device copy; every pattern's result
+    equals its own serial search, including patterns longer than the text, duplicates and capped outputs."""
+    rnd = random.Random(31337)
+    for it, chunk_mb in enumerate([None, "1", None, "1", None]):
+        if chunk_mb is None:
+            monkeypatch.delenv("BMX_H2D_CHUNK_MB", raising=False)
+        else:
+            monkeypatch.setenv("BMX_H2D_CHUNK_MB", chunk_mb)
+        sigma = rnd.choice([2, 4, 26])
+        n = rnd.choice([rnd.randint(1, 2000), rnd.randint(2000, 3_500_000)])
+        text = np.random.default_rng(it).integers(97, 97 + sigma, n, dtype=np.uint8)
+        pats = []
+        for m in [1, 2, 5, 8, 12, 40, n + 3]:
+            o = rnd.randint(0, max(n - m, 0))
+            pats.append(text[o:o + m].tobytes() if m <= n and rnd.random() < 0.7 else bytes(rnd.randrange(97, 97 + sigma) for _ in range(min(m, 1500))))
+        pats.append(pats[2])                                             # a duplicate
+        if n < 100_000:
+            pats.insert(0, b"z" * (n + 1))                               # the ingest pattern itself longer than the text
+        got = bmx.search_multi(text, pats)
+        assert len(got) == len(pats)
+        for pat, (count, pos) in zip(pats, got):
+            want = oracle.search_np(text, pat, threads=-1) if len(pat) <= n else np.zeros(0, dtype=np.int64)
+            assert count == want.size and np.array_equal(pos, want), (it, n, len(pat))
+        capped = bmx.search_multi(text.tobytes(), pats, max_positions=3)
+        for pat, (count, pos) in zip(pats, capped):
+            want = oracle.search_np(text, pat, threads=-1) if len(pat) <= n else np.zeros(0, dtype=np.int64)
+            assert count == want.size and np.array_equal(pos, want[:3])
+    assert bmx.search_multi(b"abc", []) == []
+    with pytest.raises(bmx.BmxError):
+        bmx.search_multi(b"abc", [b"a", b""])
+
+
 def test_abi_device_entry_point_raw(bmx, oracle, dev):
     """bmx_search_device exactly as a C caller would use it (ctypes, raw pointers)."""
     lib = bmx._lib.load()
