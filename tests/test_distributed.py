@@ -53,8 +53,19 @@ def _worker(rank: int, world: int, port: int, n_total: int, m: int, seed: int, o
         got = oracle.search(text.numpy().tobytes(), pattern) + pos_base
         return int(got.size), torch.from_numpy(got[:cap].copy()), {"variant": "oracle"}
 
-    total, counts, gathered, _ = bd.sharded_search(torch.from_numpy(shard), lo, pat, max_positions=1 << 20, fast_cap=fast_cap,
-                                                   local_scan=oracle_scan)
+    if fast_cap < 0:
+        # the pipelined form bench.py uses: the scan leaves {count, held, head of the list} packed in one buffer
+        # (Scanner.export_result on the GPU), the exchange is enqueued on it and awaited later
+        fast_cap = -fast_cap
+        count, pos, _ = oracle_scan(torch.from_numpy(shard), pat, lo, 1 << 20)
+        packed = torch.zeros(2 + fast_cap, dtype=torch.int64)
+        packed[0], packed[1] = count, pos.numel()
+        packed[2: 2 + min(pos.numel(), fast_cap)] = pos[:fast_cap]
+        pending = bd.combine_hits_start(None, pos, device=torch.device("cpu"), fast_cap=fast_cap, packed=packed)
+        total, counts, gathered = pending.finish()
+    else:
+        total, counts, gathered, _ = bd.sharded_search(torch.from_numpy(shard), lo, pat, max_positions=1 << 20, fast_cap=fast_cap,
+                                                       local_scan=oracle_scan)
     np.save(os.path.join(out_dir, f"count_{rank}.npy"), np.array([total] + counts, dtype=np.int64))
     if rank == 0:
         np.save(os.path.join(out_dir, "gathered.npy"), gathered.numpy())
@@ -62,7 +73,7 @@ def _worker(rank: int, world: int, port: int, n_total: int, m: int, seed: int, o
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,fast_cap", [(2, 4096), (3, 4096), (2, 5)])
+@pytest.mark.parametrize("world,fast_cap", [(2, 4096), (3, 4096), (2, 5), (2, -4096), (3, -7)])
 def test_sharded_search_equals_serial_result(world, fast_cap, tmp_path, bmx, oracle):
     import torch.multiprocessing as mp
 
