@@ -159,6 +159,136 @@ def verify_hits(torch, text, lo, pat, pos, count, cap):
     return ok
 
 
+def oracle_lib():
+    """(library, function, kind-chooser) of the CPU checker: the reference's own code where its domain allows
+    (7-bit bytes, m <= 99: oracle/_ref/libref_bm.so), else the widened restatement (oracle/liboracle.so)."""
+    so = ROOT / "oracle" / "liboracle.so"
+    if not so.exists():
+        import subprocess
+        subprocess.run(["bash", str(ROOT / "oracle" / "build_oracle.sh")], check=True, capture_output=True)
+    port = ctypes.CDLL(str(so))
+    ref_so = ROOT / "oracle" / "_ref" / "libref_bm.so"
+    ref = ctypes.CDLL(str(ref_so)) if ref_so.exists() else None
+    return port, ref
+
+
+def oracle_search(arr, pat, want_positions: bool, threads: int = -1, cap_hint: int = 0):
+    """CPU truth for a host uint8 array: (count, positions or None, kind).  All host threads, windowed."""
+    port, ref = oracle_lib()
+    n = int(arr.size)
+    legal7 = len(pat) <= 99 and max(pat) < 0x80 and (n == 0 or int(arr[: min(n, 1 << 24)].max()) < 0x80)
+    fn, kind = (ref.ref_bm_search_windowed, "reference") if (ref is not None and legal7) else (port.oracle_search_mt, "port")
+    cnt = ctypes.c_uint64()
+    cap = int(cap_hint) if want_positions else 0
+    pos = np.empty(max(cap, 1), dtype=np.int64) if want_positions else None
+    rc = fn(ctypes.c_void_p(arr.ctypes.data), ctypes.c_int64(n), ctypes.c_char_p(pat), ctypes.c_int32(len(pat)),
+            ctypes.c_void_p(pos.ctypes.data) if want_positions else None, ctypes.c_int64(cap), ctypes.byref(cnt), ctypes.c_int32(threads))
+    assert rc == 0, rc
+    return int(cnt.value), (pos[: min(int(cnt.value), cap)] if want_positions else None), kind
+
+
+def oracle_verdict(torch, text, lo, pat, count, pos, cap, dense):
+    """The CUDA result against the oracle on the same bytes (outside every timed region): the shard goes back
+    to the host, the reference's serial code (windowed over all host threads) scans it, and count + position
+    list must be identical.  Dense texts (a list of ~n positions would need 8n bytes of host memory) compare
+    the count with the oracle's and the list with its closed form on the device."""
+    host = text.cpu().numpy()
+    if dense:
+        ocount, _, kind = oracle_search(host, pat, False)
+        k = min(count, cap)
+        closed = bool((pos[:k] == torch.arange(lo, lo + k, device=pos.device, dtype=torch.int64)).all().item()) if k else True
+        return bool(ocount == count and closed and count == host.size - len(pat) + 1), f"{kind}: count + closed-form list", ocount, None
+    ocount, opos, kind = oracle_search(host, pat, True, cap_hint=max(count, 0) + 1024)
+    got = pos[: min(count, cap)].cpu().numpy() - lo if pos is not None else np.zeros(0, dtype=np.int64)
+    ok = ocount == count and (count > cap or np.array_equal(got, opos)) and np.array_equal(got, opos[: got.size])
+    return bool(ok), f"{kind}: count + full position list", ocount, opos
+
+
+def build_workload(bmx, torch, name, world, rank, dev, bytes_per_gpu=0):
+    """Materialises this rank's shard of a named workload on the device."""
+    from parallel_implementation_of_string_matching_algorithms_opencl_b200 import distributed as bd
+    w = dict(WORKLOADS[name])
+    if bytes_per_gpu:
+        w["n"] = bytes_per_gpu
+    alpha = bmx.synth.ALPHABETS[w["alphabet"]]
+    m = w["m"]
+    total_n = w["n"] * world
+    lo, hi = bd.shard_bounds(total_n, world, rank)
+    lo, end = bd.shard_read_range(total_n, m, lo, hi)
+    pat = make_pattern(bmx, w, total_n)
+    plants = plant_list(bmx, w, total_n, world)
+    text = torch.empty(end - lo, dtype=torch.uint8, device=dev)
+    bmx.synth.fill_device(text, lo, w["seed"], alpha)
+    mine = plants[(plants + m > lo) & (plants < end)]
+    bmx.synth.plant_device(text, pat, mine, base=lo)
+    torch.cuda.synchronize()
+    dense = w["alphabet"] == "a"
+    cap = (end - lo) if dense else max(4 * len(plants) + 1024, 1 << 16)
+    return dict(name=name, w=w, m=m, total_n=total_n, lo=lo, end=end, pat=pat, plants=plants, text=text, dense=dense, cap=cap)
+
+
+def kernel_roofline(W, count, scan_ms, step_gpu_ms, peak):
+    """Roofline record of the dominant kernel of one step (scan_kernel; expand_kernel when the text is dense)."""
+    n = W["end"] - W["lo"]
+    held = min(count, W["cap"])
+    kernel_ms = (step_gpu_ms - scan_ms) if W["dense"] else scan_ms
+    alg_bytes = 8 * held if W["dense"] else n      # expand writes the positions; scan reads the text
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    step_bytes = n + 8 * held
+    return {"achieved": achieved, "frac": achieved / peak, "kernel_ms": kernel_ms, "algorithmic_bytes": int(alg_bytes),
+            "kernel": "bmx::expand_kernel" if W["dense"] else "bmx::scan_kernel", "step_gpu_ms": step_gpu_ms,
+            "step_algorithmic_bytes": int(step_bytes), "step_achieved": step_bytes / (step_gpu_ms * 1e-3) / 1e9,
+            "step_frac": step_bytes / (step_gpu_ms * 1e-3) / 1e9 / peak}
+
+
+def instrumented_repeats(scanner, W, pos, stream, reps):
+    """The library's CUDA events around the scan kernel alone and around scan + expand, on the launching stream."""
+    scanner.set_timing(2)
+    scan_ms, whole_ms = [], []
+    for _ in range(reps):
+        scanner.begin(pos, stream=stream)
+        scanner.scan(W["text"], W["lo"], stream=stream)
+        c, st = scanner.finish(stream=stream)
+        scan_ms.append(st["scan_kernel_ms"])
+        whole_ms.append(st["device_ms"])
+    return c, st, float(np.mean(scan_ms)), float(np.mean(whole_ms))
+
+
+def measure_config(bmx, torch, name, dev, local, args, peak):
+    """One of the other BASELINE configs on one GPU: K back-to-back scans (device-timed), the kernel's
+    roofline, and the oracle's verdict.  Returns the entry of the line's `configs` table."""
+    W = build_workload(bmx, torch, name, 1, 0, dev)
+    pos = torch.empty(W["cap"], dtype=torch.int64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    scanner = bmx.Scanner(local)
+    scanner.set_pattern(W["pat"], variant=args.variant, stream=stream)
+    steps = max(5, min(args.steps, 20 if W["w"]["n"] >= GIB else 200))
+    scanner.set_timing(0)
+    for _ in range(3):
+        scanner.begin(pos, stream=stream)
+        scanner.scan(W["text"], W["lo"], stream=stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        scanner.begin(pos, stream=stream)
+        scanner.scan(W["text"], W["lo"], stream=stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / steps
+    count, st, scan_ms, gpu_ms = instrumented_repeats(scanner, W, pos, stream, 5)
+    ok, how, ocount, _ = oracle_verdict(torch, W["text"], W["lo"], W["pat"], count, pos, W["cap"], W["dense"])
+    ok = ok and verify_hits(torch, W["text"], W["lo"], W["pat"], pos, count, W["cap"])
+    n = W["end"] - W["lo"]
+    rf = kernel_roofline(W, count, scan_ms, gpu_ms, peak)
+    scanner.close()
+    return {"value": n / (ms_step * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_step, "steps": steps, "bytes": int(n),
+            "pattern_len": W["m"], "alphabet": W["w"]["alphabet"], "variant": st["variant"], "hits": int(count),
+            "oracle_hits": int(ocount), "verified": bool(ok), "verified_by": how,
+            "roofline": {"frac": rf["frac"], "achieved": rf["achieved"], "kernel": rf["kernel"], "kernel_ms": rf["kernel_ms"],
+                         "algorithmic_bytes": rf["algorithmic_bytes"], "step_frac": rf["step_frac"]}}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -172,43 +302,47 @@ def run_ours(args):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU path"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bd.bind_to_device_numa(local) if not args.no_numa_bind else None   # pinned text + staging threads next to the GPU's PCIe root
     if os.environ.get("NCCL_DEBUG", "VERSION") == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout (one JSON line only)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     name = args.workload or ("dna_m32_4GiB" if world == 1 else "ascii95_m64_shard")
-    w = dict(WORKLOADS[name])
-    if args.bytes_per_gpu:
-        w["n"] = args.bytes_per_gpu
-    alpha = bmx.synth.ALPHABETS[w["alphabet"]]
-    m = w["m"]
-    total_n = w["n"] * world
-    lo, hi = bd.shard_bounds(total_n, world, rank)
-    lo, end = bd.shard_read_range(total_n, m, lo, hi)
-    pat = make_pattern(bmx, w, total_n)
-    plants = plant_list(bmx, w, total_n, world)
+    W = build_workload(bmx, torch, name, world, rank, dev, args.bytes_per_gpu)
+    w, m, total_n, lo, end, pat, plants, text, dense, cap = (W[k] for k in ("w", "m", "total_n", "lo", "end", "pat", "plants", "text", "dense", "cap"))
+    peak, peak_src = peaks()
 
-    text = torch.empty(end - lo, dtype=torch.uint8, device=dev)
-    bmx.synth.fill_device(text, lo, w["seed"], alpha)
-    mine = plants[(plants + m > lo) & (plants < end)]
-    bmx.synth.plant_device(text, pat, mine, base=lo)
-    torch.cuda.synchronize()
-
-    dense = w["alphabet"] == "a"
-    cap = (end - lo) if dense else max(4 * len(plants) + 1024, 1 << 16)
     pos = torch.empty(cap, dtype=torch.int64, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     scanner = bmx.Scanner(local)
     scanner.set_pattern(pat, variant=args.variant, stream=stream)
 
-    # N > 1: the exchange of step i (one all-gather of counts + position lists, NCCL) is
-    # enqueued behind scan i and awaited only after the next scans have been queued, so the GPUs
-    # always have a scan to run while the tiny collectives and their host sync complete.
-    depth = 3 if world > 1 else 1
+    # N > 1: the exchange step runs inside the library over NVLink peer memory (bmx_exchange_*): behind scan i the
+    # post kernel stores {count, list head} into every rank's mailbox, and the collect kernel of step i-1 (sum of
+    # counts everywhere, concatenated list on rank 0) is enqueued behind it -- no collective kernel competing for
+    # SMs with the persistent scan grid, no host synchronisation inside the loop.  --exchange nccl keeps round 1's
+    # torch.distributed all-gather for comparison.
+    xchg = None
+    exchange_kind = "none"
+    if world > 1:
+        exchange_kind = args.exchange
+        if exchange_kind == "peer":
+            try:
+                xchg = bd.PeerExchange(dev, head_cap=bd.FAST_GATHER_CAP, tail_cap=(cap if dense else 0))
+            except Exception as e:   # no peer access / IPC on this box: say so and use the NCCL exchange
+                print(f"[rank {rank}] peer exchange unavailable ({e}); falling back to NCCL", file=sys.stderr, flush=True)
+                exchange_kind = "nccl (peer exchange unavailable)"
+            flag = torch.tensor([1 if xchg is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if not int(flag.item()):
+                xchg = None
+                exchange_kind = "nccl (peer exchange unavailable)"
+    gathered = [torch.empty(min(cap * world, 1 << 26) if rank == 0 else 1, dtype=torch.int64, device=dev) for _ in range(2)] if xchg else None
+    depth = 3 if (world > 1 and xchg is None) else 1
     ring = [(pos if i == 0 else torch.empty(cap, dtype=torch.int64, device=dev),
-             torch.zeros(2 + bd.FAST_GATHER_CAP, dtype=torch.int64, device=dev)) for i in range(depth)]
+             torch.zeros(2 + bd.FAST_GATHER_CAP, dtype=torch.int64, device=dev)) for i in range(depth)] if world > 1 and xchg is None else None
     inflight = []
-    state = {"i": 0, "last": None}
+    state = {"i": 0, "last": None, "host": [0.0, 0.0, 0.0]}
 
     def step():
         if world == 1:
@@ -216,20 +350,37 @@ def run_ours(args):
             scanner.scan(text, lo, stream=stream)
             return
         t0 = time.perf_counter()
+        i = state["i"]
+        state["i"] += 1
+        if xchg is not None:
+            scanner.begin(pos, stream=stream)
+            scanner.scan(text, lo, stream=stream)
+            t1 = time.perf_counter()
+            xchg.post(scanner, stream)
+            t2 = time.perf_counter()
+            if i > 0:
+                state["seq"] = xchg.collect(gathered[(i - 1) & 1] if rank == 0 else None, stream)
+            t3 = time.perf_counter()
+            state["host"] = [a + b for a, b in zip(state["host"], (t1 - t0, t2 - t1, t3 - t2))]
+            return
         if len(inflight) == depth:
             state["last"] = inflight.pop(0).finish()
         t1 = time.perf_counter()
-        p_i, packed_i = ring[state["i"] % depth]
-        state["i"] += 1
+        p_i, packed_i = ring[i % depth]
         scanner.begin(p_i, stream=stream)
         scanner.scan(text, lo, stream=stream)
         scanner.export_result(packed_i, stream=stream)
         t2 = time.perf_counter()
         inflight.append(bd.combine_hits_start(None, p_i, group=None, device=dev, packed=packed_i))
         t3 = time.perf_counter()
-        state["host"] = [a + b for a, b in zip(state.get("host", [0.0, 0.0, 0.0]), (t1 - t0, t2 - t1, t3 - t2))]
+        state["host"] = [a + b for a, b in zip(state["host"], (t1 - t0, t2 - t1, t3 - t2))]
 
     def drain():
+        if xchg is not None:
+            if state["i"] > 0:
+                state["seq"] = xchg.collect(gathered[(state["i"] - 1) & 1] if rank == 0 else None, stream)
+                state["i"] = 0       # the next step() starts a fresh post/collect pairing
+            return
         while inflight:
             state["last"] = inflight.pop(0).finish()
 
@@ -244,124 +395,166 @@ def run_ours(args):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scanner.set_timing(0)          # no event records between the kernels of the headline loop (they cost ~10 us/step)
+    state["host"] = [0.0, 0.0, 0.0]
     with ClockSampler(local) as clk:
+        t_host0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
             step()
         drain()
         e1.record()
+        t_host1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t_host2 = time.perf_counter()
         if world > 1:
             dist.barrier()
-        torch.cuda.synchronize()
     count, stats = scanner.finish(stream=stream)
-    ms_total = e0.elapsed_time(e1)
+    ms_total = ms_local = e0.elapsed_time(e1)
     total_hits = count
+    counts_all, gathered_len, gathered_list = [count], min(count, cap), (pos[: min(count, cap)] if world == 1 else None)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-        if state["last"] is not None:
-            total_hits = state["last"][0]
-            ok = ok and state["last"][0] == sum(state["last"][1])
+        if xchg is not None:
+            total_hits, counts_all, gathered_len = xchg.wait(state["seq"])
+            if rank == 0:
+                gathered_list = gathered[(args.steps - 1) & 1][:gathered_len]
+        elif state["last"] is not None:
+            total_hits, counts_all, gathered_list = state["last"]
+            gathered_len = 0 if gathered_list is None else int(gathered_list.numel())
+        ok = ok and total_hits == sum(counts_all) and counts_all[rank] == count
     ms_step = ms_total / args.steps
     value = total_n / (ms_step * 1e-3) / 1e9
 
-    # instrumented repeat of the same steps (local scan only): the library's CUDA events around the scan
-    # kernel alone and around memset + scan + expand, on the launching stream, averaged over the repeats
-    scanner.set_timing(2)
+    # instrumented repeat of the same steps (local scan only), right after the timed loop
     torch.cuda.synchronize()
     kreps = max(3, min(args.steps, 20))
-    scan_ms, whole_ms = [], []
-    for _ in range(kreps):
-        scanner.begin(pos, stream=stream)
-        scanner.scan(text, lo, stream=stream)
-        _c, st_i = scanner.finish(stream=stream)
-        scan_ms.append(st_i["scan_kernel_ms"])
-        whole_ms.append(st_i["device_ms"])
-    stats = st_i
-    stats_scan_ms = float(np.mean(scan_ms))
-    step_gpu_ms = float(np.mean(whole_ms))
-
-    # roofline of the dominant kernel (scan_kernel; expand_kernel when the text is dense): CUDA events
-    # recorded by the library on the launching stream around that kernel, inside the timed region
-    peak, peak_src = peaks()
-    dense_text = dense
-    kernel_ms = (step_gpu_ms - stats_scan_ms) if dense_text else stats_scan_ms
-    alg_bytes = 8 * min(count, cap) if dense_text else (end - lo)   # expand writes the positions; scan reads the text
-    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    step_bytes = (end - lo) + 8 * min(count, cap)
+    _c, stats, stats_scan_ms, step_gpu_ms = instrumented_repeats(scanner, W, pos, stream, kreps)
+    rf = kernel_roofline(W, count, stats_scan_ms, step_gpu_ms, peak)
     traffic = None
-    tf = ROOT / "profiles" / "r01_traffic.json"
-    if tf.exists():
-        rec = json.loads(tf.read_text()).get(name)
-        if rec and not args.bytes_per_gpu:
-            traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
+    for tf in (ROOT / "profiles" / "r02_traffic.json", ROOT / "profiles" / "r01_traffic.json"):
+        if tf.exists() and traffic is None:
+            rec = json.loads(tf.read_text()).get(name)
+            if rec and not args.bytes_per_gpu:
+                traffic = rec["dram_read_bytes"] + rec["dram_write_bytes"]
 
-    # ---- e2e: host-pointer C-ABI call, pinned host text, H2D + scan + D2H inside the timed region
-    e2e = None
+    # ---- the oracle's verdict (outside every timed region): every rank's local result against the reference's
+    # serial code on the same shard; rank 0's gathered list against the rank-ordered concatenation of the oracle lists
+    verified_by = "not run (--no-verify)"
+    oracle_hits = None
+    if not args.no_verify:
+        ok_local, verified_by, ocount, opos = oracle_verdict(torch, text, lo, pat, count, pos, cap, dense)
+        ok = ok and ok_local
+        oracle_hits = ocount
+        if world > 1:
+            lists = [None] * world
+            dist.all_gather_object(lists, (int(ocount), None if opos is None else (opos + lo)))
+            oracle_hits = sum(c for c, _ in lists)
+            ok = ok and oracle_hits == total_hits
+            if rank == 0 and not dense and gathered_list is not None:
+                want = np.concatenate([p for _, p in lists])
+                ok = ok and np.array_equal(gathered_list.cpu().numpy(), want[:gathered_len]) and gathered_len == min(want.size, gathered[0].numel() if xchg else want.size)
+            flag = torch.tensor([1 if ok else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            ok = bool(flag.item())
+            verified_by += f"; every rank's shard + the gathered list on rank 0 ({world} ranks)"
+
+    # ---- e2e: host-pointer C-ABI call, H2D + scan + D2H inside the timed region (pinned text; pageable text
+    # -- the reference's own calling pattern, std::string -> malloc copy, BoyreMoore.cpp:77-90 -- at N = 1)
+    e2e = e2e_pageable = None
+    host_sample = None
     if not args.no_e2e:
         host_text = torch.empty(end - lo, dtype=torch.uint8, pin_memory=True)
         host_text.copy_(text)
         torch.cuda.synchronize()
         e2e_cap = min(cap, 1 << 24)
         e2e_steps = max(2, min(args.steps, args.e2e_steps))
-        bmx.search(host_text, pat, max_positions=e2e_cap, device=local)     # warm-up (allocations, pool)
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            c2, p2 = bmx.search(host_text, pat, max_positions=e2e_cap, device=local)
+
+        def e2e_run(src, label):
+            bmx.search(src, pat, max_positions=e2e_cap, device=local)     # warm-up (allocations)
             if world > 1:
-                bd.combine_hits(c2, torch.from_numpy(p2 + lo).to(dev), group=None, device=dev)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
+                dist.barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                c2, p2 = bmx.search(src, pat, max_positions=e2e_cap, device=local)
+                if world > 1:
+                    bd.combine_hits(c2, torch.from_numpy(p2 + lo).to(dev), group=None, device=dev)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            return c2, {"value": total_n / (dt / e2e_steps) / 1e9, "unit": "GB/s", "steps": e2e_steps,
+                        "h2d_bytes_per_step": int(end - lo) + len(pat) + 1024 + 4 * len(pat),
+                        "d2h_bytes_per_step": 8 * int(min(c2, e2e_cap)) + 8, "api": f"bmx_search_ex (host pointers, {label} text)"}
+
+        c2, e2e = e2e_run(host_text, "pinned")
         ok = ok and c2 == count
-        e2e = {"value": total_n / (dt / e2e_steps) / 1e9, "unit": "GB/s", "steps": e2e_steps,
-               "h2d_bytes_per_step": int(end - lo) + len(pat) + 1024 + 4 * len(pat),
-               "d2h_bytes_per_step": 8 * int(min(c2, e2e_cap)) + 8,
-               "api": "bmx_search_ex (host pointers, pinned text)"}
         host_sample = host_text
-    else:
-        host_sample = None
+        if world == 1 and not args.no_pageable:
+            pageable = host_text.numpy().copy()
+            c3, e2e_pageable = e2e_run(pageable, "pageable")
+            ok = ok and c3 == count
+            del pageable
 
     # ---- cpu_baseline: the reference's own serial code on a bounded sample (rank 0, N = 1)
     cpu = None
     if world == 1 and not args.no_cpu and rank == 0:
         cpu = cpu_baseline(host_sample if host_sample is not None else text.cpu(), pat, threads=1,
                            sample_bytes=args.cpu_sample_bytes)
+        if cpu["sample_bytes"] == end - lo:
+            ok = ok and cpu["hits"] == count       # the baseline leg scanned the whole text: same count
 
-    if os.environ.get("BENCH_DEBUG") and "host" in state:
-        n_steps = max(state["i"], 1)
-        print(f"[rank {rank}] host ms/step: finish(oldest)={state['host'][0] / n_steps * 1e3:.3f} "
-              f"scan-enqueue={state['host'][1] / n_steps * 1e3:.3f} collectives-enqueue={state['host'][2] / n_steps * 1e3:.3f}",
-              file=sys.stderr, flush=True)
+    if os.environ.get("BENCH_DEBUG"):
+        n_steps = max(args.steps, 1)
+        print(f"[rank {rank}] numa={numa} exchange={exchange_kind} gpu_ms(local events)={ms_local:.3f} max-over-ranks={ms_total:.3f} "
+              f"step_gpu_ms={step_gpu_ms:.4f} host enqueue of {n_steps} steps={(t_host1 - t_host0) * 1e3:.3f} ms "
+              f"(scan {state['host'][0] / n_steps * 1e6:.1f} us, post {state['host'][1] / n_steps * 1e6:.1f} us, collect {state['host'][2] / n_steps * 1e6:.1f} us per step) "
+              f"sync after enqueue={(t_host2 - t_host1) * 1e3:.3f} ms", file=sys.stderr, flush=True)
+
+    # ---- the other BASELINE configs (N = 1): same protocol, one entry each in `configs`
+    configs = None
+    if world == 1 and not args.no_configs and not args.workload:
+        del text, pos
+        W["text"] = None
+        torch.cuda.empty_cache()
+        configs = {name: {"value": value, "unit": "GB/s", "ms_per_step": ms_step, "steps": args.steps, "bytes": int(end - lo),
+                          "pattern_len": m, "alphabet": w["alphabet"], "variant": stats["variant"], "hits": int(total_hits),
+                          "oracle_hits": oracle_hits, "verified": bool(ok), "verified_by": verified_by,
+                          "roofline": {k: rf[k] for k in ("frac", "achieved", "kernel", "kernel_ms", "algorithmic_bytes", "step_frac")}}}
+        for other in ("ascii95_m16_64MiB", "bytes256_m4_4GiB", "bytes256_m16_4GiB", "bytes256_m128_4GiB", "aaa_1GiB", "ascii95_m64_shard"):
+            configs[other] = measure_config(bmx, torch, other, dev, local, args, peak)
+            torch.cuda.empty_cache()
+
     if rank == 0:
+        launches_per_step = 2 if world == 1 else (4 if xchg is not None else 3)
         line = {
             "metric": "text GB/s scanned (device-timed)", "value": value, "unit": "GB/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
             "config": {"workload": name, "bytes_per_gpu": int(w["n"]), "total_bytes": int(total_n), "pattern_len": m,
-                       "alphabet": w["alphabet"], "plants": int(len(plants)), "hits": int(total_hits),
+                       "alphabet": w["alphabet"], "plants": int(len(plants)), "hits": int(total_hits), "oracle_hits": oracle_hits,
                        "variant": stats["variant"], "tile_bytes": stats["tile_bytes"], "stages": stats["stages"],
                        "grid": stats["grid"], "l2": "inputs larger than L2 (no flush needed)" if w["n"] > (256 << 20) else "input fits L2: flushless, see DESIGN.md",
-                       "verified": bool(ok), "parallelism": f"shard{world}" if world > 1 else "single"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": kernel_ms,
-                         "algorithmic_bytes": int(alg_bytes), "kernel": "bmx::expand_kernel" if dense_text else "bmx::scan_kernel",
+                       "verified": bool(ok), "verified_by": verified_by, "exchange": exchange_kind,
+                       "numa_node": numa, "parallelism": f"shard{world}" if world > 1 else "single"},
+            "roofline": {"bound": "hbm", "achieved": rf["achieved"], "peak": peak, "unit": "GB/s", "frac": rf["frac"],
+                         "traffic": traffic, "peak_source": peak_src, "kernel_ms": rf["kernel_ms"],
+                         "algorithmic_bytes": rf["algorithmic_bytes"], "kernel": rf["kernel"],
                          "kernel_timing": f"CUDA events recorded by libbmx around the kernel, mean of {kreps} instrumented repeats right after the timed loop",
-                         "step_gpu_ms": step_gpu_ms, "step_algorithmic_bytes": int(step_bytes),
-                         "step_achieved": step_bytes / (step_gpu_ms * 1e-3) / 1e9,
-                         "step_frac": step_bytes / (step_gpu_ms * 1e-3) / 1e9 / peak},
-            "e2e": e2e, "gpu_launches": int(args.steps) * 2, "clocks": clk.summary(), "cpu_baseline": cpu,
+                         "step_gpu_ms": rf["step_gpu_ms"], "step_algorithmic_bytes": rf["step_algorithmic_bytes"],
+                         "step_achieved": rf["step_achieved"], "step_frac": rf["step_frac"]},
+            "e2e": e2e, "e2e_pageable": e2e_pageable, "gpu_launches": int(args.steps) * launches_per_step,
+            "clocks": clk.summary(), "cpu_baseline": cpu, "configs": configs,
         }
         emit(line)
     scanner.close()
     if world > 1:
         dist.barrier()
+        if xchg is not None:
+            xchg.close()
         dist.destroy_process_group()
 
 
@@ -389,7 +582,8 @@ def cpu_baseline(host_text, pat, threads: int, sample_bytes: int):
     dt = time.perf_counter() - t0
     assert rc == 0, rc
     return {"value": n / dt / 1e9, "unit": "GB/s", "cores": threads if threads > 0 else os.cpu_count(), "kind": kind,
-            "sample": f"first {n} bytes of the workload text, {cnt.value} hits, {dt:.2f} s", "host_cores_total": os.cpu_count()}
+            "sample": f"first {n} bytes of the workload text, {cnt.value} hits, {dt:.2f} s", "host_cores_total": os.cpu_count(),
+            "hits": int(cnt.value), "sample_bytes": n}
 
 
 def run_reference(args):
@@ -466,6 +660,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle comparison (outside the timed regions)")
+    ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the other BASELINE configs")
+    ap.add_argument("--no-pageable", action="store_true", help="N = 1: skip the pageable-text e2e leg")
+    ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: exchange step over peer memory (library) or NCCL all-gather")
     ap.add_argument("--cpu-sample-bytes", type=int, default=4 * GIB)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define BMX_VERSION 100 /* 0.1.0 */
+#define BMX_VERSION 200 /* 0.2.0 */
 
 typedef enum bmx_status {
     BMX_OK = 0,
@@ -37,7 +37,8 @@ typedef enum bmx_status {
     BMX_E_CUDA = -2,      /* a CUDA runtime call failed; see bmx_last_error() */
     BMX_E_NOMEM = -3,     /* host or device allocation failed */
     BMX_E_NODEVICE = -4,  /* no CUDA device visible */
-    BMX_E_TABLES = -5     /* caller-supplied gs/bs tables differ from the ones this pattern needs */
+    BMX_E_TABLES = -5,    /* caller-supplied gs/bs tables differ from the ones this pattern needs */
+    BMX_E_EXCHANGE = -6   /* multi-GPU exchange step failed: no peer access, IPC mapping failed, or a peer timed out */
 } bmx_status;
 
 /* Longest supported pattern (the reference stops at 99: char word[100], BoyreMoore.cpp:144). */
@@ -70,6 +71,17 @@ const char *bmx_last_error(void);
 
 /* Number of visible CUDA devices (0 when there is none; never fails). */
 int bmx_device_count(void);
+
+/*
+ * Device memory policy.  The convenience calls (bmx_search*, bmx_find_first*, bmx_search_partitions,
+ * bmx_search_multi) keep, per calling host thread and device, one device buffer for the text and one for the
+ * positions (plain cudaMalloc blocks, grown on demand, never sized by the 8-bytes-per-text-byte worst case)
+ * plus pinned staging buffers, so that repeated calls do not allocate.  The library does not change any
+ * attribute of the device's memory pools.  bmx_release_memory gives the calling thread's cached buffers for
+ * `device` (< 0: every device) back to the driver; a host thread that exits releases everything it held.
+ * (The reference allocates and releases its six cl_mem buffers on every iteration, BoyreMoore.cpp:233-244,299-310.)
+ */
+int bmx_release_memory(int device);
 
 /*
  * Pattern pre-processing, once per pattern -- replaces BoyreMoore.cpp:153-162 (bad-symbol
@@ -222,6 +234,60 @@ void bmx_mg_destroy(bmx_mg *mg);
 int bmx_mg_device_count(const bmx_mg *mg);
 int bmx_mg_search(bmx_mg *mg, const char *text, int64_t n, const char *pat, int32_t m,
                   int64_t *pos_out, int64_t pos_cap, uint64_t *count_out, uint64_t *shard_counts);
+
+/*
+ * The exchange step of the sharded scan, inside the library, over NVLink peer memory -- no NCCL
+ * kernel, no host synchronisation per step.  The reference has nothing of the kind: one device
+ * (BoyreMoore.cpp:217-219), word ranges without overlap (:119-141), per-range counts read back with a blocking
+ * clEnqueueReadBuffer (:286).
+ *
+ * One bmx_exchange per rank (= GPU).  Every rank owns a small device "mailbox"; bmx_exchange_post stores this
+ * rank's {count, list head} into the mailboxes of its peers with plain stores through peer pointers and
+ * publishes the step number behind a system-scope release; bmx_exchange_collect waits (on the device) for the
+ * world's step numbers, sums the counts and -- on rank dst -- concatenates the position lists in rank order
+ * (= ascending order) into d_out.  Both calls only enqueue a kernel on `stream`; bmx_exchange_wait polls a
+ * host-mapped result word, it performs no CUDA call on the fast path.
+ *
+ * Ranks may be threads of one process (bmx_exchange_connect_local; peer access is enabled as needed) or one
+ * process per GPU (torchrun): each rank publishes bmx_exchange_handle (a cudaIpcMemHandle, 64 bytes), the
+ * handles travel by any means (distributed.py uses one torch.distributed all_gather at set-up) and
+ * bmx_exchange_connect maps them.  head_cap positions per rank ride along with the header (ring of `depth`
+ * steps); longer lists use the single-buffered tail area (tail_cap positions per source, on dst only).  The
+ * gathered list is always a prefix of the global ascending list: it ends behind the first rank whose list did
+ * not fit (its own pos_cap, or head_cap + tail_cap); the total count is exact regardless.
+ *
+ * Call order per rank and step: bmx_scanner_begin/scan ... -> bmx_exchange_post -> (later) bmx_exchange_collect;
+ * at most depth-1 steps may be posted and not yet collected.  Collecting step q-1 after posting step q keeps
+ * every GPU from ever waiting for a peer.  Device-side waits time out after BMX_XCHG_TIMEOUT_MS (default
+ * 20000) and surface as BMX_E_EXCHANGE from bmx_exchange_wait.  All ranks must be connected before the first
+ * post and idle before any rank is destroyed (a barrier of the caller's choice).
+ */
+#define BMX_EXCHANGE_HANDLE_BYTES 64
+#define BMX_EXCHANGE_MAX_RANKS 16
+typedef struct bmx_exchange bmx_exchange;
+int bmx_exchange_create(int device, int rank, int world, int dst, int64_t head_cap, int64_t tail_cap, int depth,
+                        bmx_exchange **out);
+void bmx_exchange_destroy(bmx_exchange *x);
+int bmx_exchange_handle(bmx_exchange *x, void *handle_out /* BMX_EXCHANGE_HANDLE_BYTES */);
+int bmx_exchange_connect(bmx_exchange *x, const void *handles /* world x BMX_EXCHANGE_HANDLE_BYTES, rank order */);
+int bmx_exchange_connect_local(bmx_exchange *const *all /* world exchanges of this process, rank order */, int world);
+/* Ships the running result of `s` (count + the positions it holds) as the next step; *seq_out = its number (1, 2, ...). */
+int bmx_exchange_post(bmx_exchange *x, bmx_scanner *s, void *stream, uint64_t *seq_out);
+/* Completes the oldest uncollected step; d_out/out_cap (DEVICE memory) are used on rank dst only. */
+int bmx_exchange_collect(bmx_exchange *x, int64_t *d_out, int64_t out_cap, void *stream, uint64_t *seq_out);
+/* Blocks the calling host thread until step `seq` has been collected on this rank.  counts_out: world entries. */
+int bmx_exchange_wait(bmx_exchange *x, uint64_t seq, uint64_t *total_out, uint64_t *counts_out, int64_t *gathered_out);
+
+/*
+ * Device-resident multi-GPU search (BASELINE config 5 from C): shard r lives on GPU r of `mg` as
+ * d_text[r][0 .. n[r]) = its own start positions plus the (m-1)-byte halo, pos_base[r] = global offset of its
+ * first byte.  Every GPU scans its shard, the exchange step above combines the counts and gathers the lists on
+ * GPU 0 of `mg`: d_pos_out (DEVICE memory on that GPU, may be NULL) receives the first min(count, pos_cap)
+ * global positions, ascending.  shard_counts (optional): ngpus entries.  Synchronous.
+ */
+int bmx_mg_search_device(bmx_mg *mg, const void *const *d_text, const int64_t *n, const int64_t *pos_base,
+                         const char *pat, int32_t m, int64_t *d_pos_out, int64_t pos_cap, uint64_t *count_out,
+                         uint64_t *shard_counts);
 
 /*
  * Synthetic text generator used by the tests and bench.py (identical definition on the CPU in

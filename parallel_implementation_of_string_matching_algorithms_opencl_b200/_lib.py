@@ -16,6 +16,7 @@ BMX_E_CUDA = -2
 BMX_E_NOMEM = -3
 BMX_E_NODEVICE = -4
 BMX_E_TABLES = -5
+BMX_E_EXCHANGE = -6
 
 VARIANT_AUTO = 0
 VARIANT_QGRAM = 1
@@ -23,13 +24,15 @@ VARIANT_WINDOW = 2
 VARIANT_SHIFTAND = 3
 VARIANT_NAMES = {0: "auto", 1: "qgram", 2: "window", 3: "shiftand"}
 
-# every symbol include/bmx.h declares (tests/test_abi.py checks the header against this list)
+# every symbol include/bmx.h declares (tests/test_host_logic.py checks the header against this list)
 EXPORTS = [
     "bmx_version", "bmx_last_error", "bmx_device_count", "bmx_build_tables", "bmx_search",
     "bmx_search_ex", "bmx_search_device", "bmx_search_device_ex", "bmx_search_partitions",
     "bmx_find_first", "bmx_find_first_device", "bmx_search_multi",
     "bmx_scanner_create", "bmx_scanner_destroy", "bmx_scanner_set_pattern", "bmx_scanner_begin",
     "bmx_scanner_scan", "bmx_scanner_finish", "bmx_scanner_export_result", "bmx_scanner_set_timing", "bmx_mg_create", "bmx_mg_destroy", "bmx_mg_device_count", "bmx_mg_search", "bmx_synth_fill_device", "bmx_partition_words",
+    "bmx_mg_search_device", "bmx_exchange_create", "bmx_exchange_destroy", "bmx_exchange_handle", "bmx_exchange_connect",
+    "bmx_exchange_connect_local", "bmx_exchange_post", "bmx_exchange_collect", "bmx_exchange_wait", "bmx_release_memory",
 ]
 
 
@@ -106,6 +109,18 @@ def load() -> ctypes.CDLL:
     lib.bmx_mg_device_count.argtypes = [c_void_p]
     lib.bmx_mg_device_count.restype = c_int
     lib.bmx_mg_search.argtypes = [c_void_p, c_void_p, c_int64, c_char_p, c_int32, c_void_p, c_int64, POINTER(c_uint64), POINTER(c_uint64)]
+    lib.bmx_mg_search_device.argtypes = [c_void_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int64), c_char_p, c_int32,
+                                         c_void_p, c_int64, POINTER(c_uint64), POINTER(c_uint64)]
+    lib.bmx_exchange_create.argtypes = [c_int, c_int, c_int, c_int, c_int64, c_int64, c_int, POINTER(c_void_p)]
+    lib.bmx_exchange_destroy.argtypes = [c_void_p]
+    lib.bmx_exchange_destroy.restype = None
+    lib.bmx_exchange_handle.argtypes = [c_void_p, c_void_p]
+    lib.bmx_exchange_connect.argtypes = [c_void_p, c_void_p]
+    lib.bmx_exchange_connect_local.argtypes = [POINTER(c_void_p), c_int]
+    lib.bmx_exchange_post.argtypes = [c_void_p, c_void_p, c_void_p, POINTER(c_uint64)]
+    lib.bmx_exchange_collect.argtypes = [c_void_p, c_void_p, c_int64, c_void_p, POINTER(c_uint64)]
+    lib.bmx_exchange_wait.argtypes = [c_void_p, c_uint64, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_int64)]
+    lib.bmx_release_memory.argtypes = [c_int]
     lib.bmx_synth_fill_device.argtypes = [c_void_p, c_int64, c_int64, c_uint64, c_char_p, c_int32, c_void_p]
     for name in EXPORTS:
         fn = getattr(lib, name)

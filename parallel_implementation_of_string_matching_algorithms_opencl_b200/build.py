@@ -15,8 +15,8 @@ CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "libbmx.so"
 REFMAIN_PATH = PKG_DIR / "bmx_refmain"
 
-SOURCES = ["bmx_scan.cu", "bmx_abi.cu", "bmx_tables.cpp", "bmx_partition.cpp"]
-HEADERS = ["bmx_internal.h", "../../include/bmx.h"]
+SOURCES = ["bmx_scan.cu", "bmx_abi.cu", "bmx_host.cu", "bmx_multi.cu", "bmx_exchange.cu", "bmx_tables.cpp", "bmx_partition.cpp"]
+HEADERS = ["bmx_internal.h", "bmx_scanner.h", "bmx_ctx.h", "../../include/bmx.h"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17",
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -40,13 +40,28 @@ def _stale(target: Path, deps: list[Path]) -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile libbmx.so (and the bmx_refmain demo) if missing or older than its sources."""
-    deps = [CSRC / s for s in SOURCES] + [CSRC / h for h in HEADERS]
-    if force or _stale(LIB_PATH, deps):
-        cmd = [_nvcc(), *NVCC_FLAGS, "-shared", "-o", str(LIB_PATH), *[str(CSRC / s) for s in SOURCES]]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-        subprocess.run(cmd, check=True, cwd=CSRC)
+    """Compile libbmx.so (and the bmx_refmain demo) if missing or older than its sources.
+    One object per source (compiled in parallel, only the stale ones), then one link."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    headers = [CSRC / h for h in HEADERS]
+    objdir = CSRC / "build"
+    objdir.mkdir(exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src: str) -> Path:
+        obj = objdir / (src.rsplit(".", 1)[0] + ".o")
+        if force or _stale(obj, [CSRC / src, *headers]):
+            cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", str(obj), str(CSRC / src)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            subprocess.run(cmd, check=True, cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    if force or _stale(LIB_PATH, objs):
+        subprocess.run([nvcc, *NVCC_FLAGS, "-shared", "-o", str(LIB_PATH), *[str(o) for o in objs]], check=True, cwd=CSRC)
     refmain_src = CSRC / "bmx_refmain.cpp"
     if refmain_src.exists() and (force or _stale(REFMAIN_PATH, [refmain_src, LIB_PATH])):
         cmd = ["g++", "-O2", "-std=c++17", "-o", str(REFMAIN_PATH), str(refmain_src),

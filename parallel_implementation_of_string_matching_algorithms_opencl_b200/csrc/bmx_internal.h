@@ -78,6 +78,11 @@ struct ScanArgs {
     unsigned long long *carry_out;         // carry_in + hits of this scan (block-scan kernel)
     unsigned long long *count_acc;         // count-only mode: running total over the chained scans (last CTA adds scan_count)
     unsigned long long *scan_count;        // count-only mode: this scan's hits, atomically accumulated; zeroed per launch
+    unsigned long long *host_count;        // host-mapped word: the last CTA of every scan also stores the running count there (finish() reads it without a copy)
+    // find-first mode (count-only kernels): key = epoch << 47 | (2^47-1 - position), combined with atomicMax, so a
+    // stale word of an earlier search never needs clearing; producers stop fetching tiles behind the best hit
+    unsigned long long *first_key;
+    uint32_t find_epoch;                   // 0: not a find-first scan
     uint32_t first_scan;                   // first scan of a search: carry_in / count_acc count as 0 (no memset needed)
     void *zero_ptr;                        // expand kernel: the OTHER zero-initialised scratch half, left dirty by the scan before
     uint32_t zero_vec16;                   //   this one; its first zero_vec16 16-byte words are cleared for the next scan (0: nothing)
@@ -107,5 +112,6 @@ int launch_partition_count(const int64_t *d_pos, const unsigned long long *d_cou
 void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, ScanArgs *args);
 
 constexpr uint32_t kHashMul = 0x9E3779B1u;
+constexpr unsigned long long kFindMask = (1ull << 47) - 1;   // find-first keys: positions below 2^47
 
 }  // namespace bmx

@@ -335,6 +335,27 @@ __device__ __forceinline__ uint32_t publish_segment(const ScanArgs &A, uint32_t 
     return total;
 }
 
+// find-first mode: the smallest start position among this warp's hits of one segment goes into the search's key word.
+// Positions of one segment order as slab * 512 + lane * 16 + bit, so a 32-bit warp minimum finds the smallest.
+__device__ __forceinline__ void report_first(const ScanArgs &A, const uint32_t (&hm)[4], int64_t seg_v0, int lane)
+{
+    uint32_t off = 0xFFFFFFFFu;
+#pragma unroll
+    for (int sl = 3; sl >= 0; --sl)
+        if (hm[sl]) off = sl * 512 + lane * 16 + (__ffs(hm[sl]) - 1);
+    off = __reduce_min_sync(0xFFFFFFFFu, off);
+    if (lane == 0 && off != 0xFFFFFFFFu) {
+        const unsigned long long p = (unsigned long long)(seg_v0 + off + A.pos_bias);
+        atomicMax(A.first_key, ((unsigned long long)A.find_epoch << 47) | (kFindMask - (p & kFindMask)));
+    }
+}
+// The smallest position reported so far in this search, or -1.
+__device__ __forceinline__ long long first_so_far(const ScanArgs &A)
+{
+    const unsigned long long k = __ldcg(A.first_key);
+    return (uint32_t)(k >> 47) == A.find_epoch ? (long long)(kFindMask - (k & kFindMask)) : -1ll;
+}
+
 // A warp switches to dense_tile() for its next tile when, on average, this many of its lanes held
 // candidates in each segment of the current tile: then the any-pass + vote + recompute of the sparse
 // path costs more than building every lane's masks right away.
@@ -378,6 +399,7 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
         cand_lanes += __popc(__ballot_sync(0xFFFFFFFFu, any_cand != 0));
         const uint32_t hit_lanes = __ballot_sync(0xFFFFFFFFu, seg_hits != 0);
         found += seg_hits;
+        if (!POSITIONS && A.find_epoch && hit_lanes) report_first(A, hm, tile_v0 + seg_off + OFFS, lane);
         if (POSITIONS && hit_lanes) tile_total += publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
     }
     if (POSITIONS && tile_total && lane == 0)
@@ -461,7 +483,11 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         for (uint32_t it = 1;; ++it) {
             const uint32_t s = it % S;
             const uint32_t tile = next_tile;
-            const bool live = tile < A.num_tiles;
+            bool live = tile < A.num_tiles;
+            if (!POSITIONS && A.find_epoch && live) {  // find-first: nothing at or behind a tile that starts past the best hit can win
+                const long long found = first_so_far(A);
+                if (found >= 0 && (long long)tile * TILE + OFFS + A.pos_bias > found) live = false;
+            }
             if (live) next_tile = gridDim.x + atomicAdd(A.tile_counter, 1u);  // ticket for the next round, in flight during the wait
             mbar_wait(&ctl->empty[s], ((it / S) & 1u) ^ 1u);
             if (!live) {
@@ -542,8 +568,10 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                     }
                 }
                 if (has_hits) {
-                    if (!POSITIONS) my_count += seg_hits;
-                    else tile_total += publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
+                    if (!POSITIONS) {
+                        my_count += seg_hits;
+                        if (A.find_epoch) report_first(A, hm, tile_v0 + seg_off + OFFS, lane);
+                    } else tile_total += publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
                 }
             }
             if (POSITIONS && tile_total && lane == 0)  // a warp's 4 KiB of a tile lie inside one 2 MiB block
@@ -564,7 +592,12 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         bar_sync_consumers();
         if (tid == 0 && atomicAdd(A.tile_counter + 1, 1u) == gridDim.x - 1) {
             __threadfence();
-            *A.count_acc = (A.first_scan ? 0ull : *A.count_acc) + __ldcg(A.scan_count);
+            const unsigned long long running = (A.first_scan ? 0ull : *A.count_acc) + __ldcg(A.scan_count);
+            *A.count_acc = running;
+            if (A.host_count) {
+                A.host_count[0] = running;
+                if (A.find_epoch) A.host_count[1] = (unsigned long long)first_so_far(A);
+            }
             // leave the header as it was found (all zero): a count-only scan needs no memset before the next one
             A.tile_counter[0] = 0u;
             A.tile_counter[1] = 0u;
@@ -641,7 +674,9 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         bar_sync_consumers();  // scan_warp / scan_dense are rewritten by the next chunk
     }
     if (tid == 0) {
-        *A.carry_out = (A.first_scan ? 0ull : *A.carry_in) + hits_carry;
+        const unsigned long long running = (A.first_scan ? 0ull : *A.carry_in) + hits_carry;
+        *A.carry_out = running;
+        if (A.host_count) *A.host_count = running;
         A.tile_counter[3] = dense_carry;
     }
 }
@@ -1133,30 +1168,45 @@ static const void *pick_kernel(int variant, bool full8, int tile, bool positions
     }
 }
 
-int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, ScanLaunch *out)
+// Device attributes (and the expand kernel's occupancy) are queried once per device, under a mutex: a search on
+// a 500 KB text is launch-latency bound, and the entry points may be called from one host thread per GPU.
+static std::mutex dev_mutex;
+
+static int device_info(int device, int *sm_count, int *smem_optin, int *smem_sm, int *expand_per_sm)
 {
-    // device attributes are queried once per device (a search on a 500 KB text is launch-latency bound)
     struct DevInfo {
-        int sm_count = 0, smem_optin = 0, smem_sm = 0;
+        int sm_count = 0, smem_optin = 0, smem_sm = 0, expand_per_sm = 0;
     };
     static DevInfo dev_info[64];
-    static std::mutex dev_mutex;
-    int sm_count, smem_optin, smem_sm;
-    {
-        std::lock_guard<std::mutex> lock(dev_mutex);
-        DevInfo &di = dev_info[device & 63];
-        if (di.sm_count == 0) {
-            if (cudaDeviceGetAttribute(&di.sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
-                cudaDeviceGetAttribute(&di.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
-                cudaDeviceGetAttribute(&di.smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device) != cudaSuccess) {
-                di = DevInfo{};
-                return fail(BMX_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
-            }
+    std::lock_guard<std::mutex> lock(dev_mutex);
+    DevInfo &di = dev_info[device & 63];
+    if (di.sm_count == 0) {
+        DevInfo q;
+        if (cudaDeviceGetAttribute(&q.sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+            cudaDeviceGetAttribute(&q.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) != cudaSuccess ||
+            cudaDeviceGetAttribute(&q.smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, device) != cudaSuccess)
+            return fail(BMX_E_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(cudaGetLastError()));
+        int cur = 0;
+        cudaGetDevice(&cur);
+        if (cur != device) cudaSetDevice(device);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q.expand_per_sm, expand_kernel, kExpandThreads, 0) != cudaSuccess || q.expand_per_sm < 1) {
+            (void)cudaGetLastError();
+            q.expand_per_sm = 2;
         }
-        sm_count = di.sm_count;
-        smem_optin = di.smem_optin;
-        smem_sm = di.smem_sm;
+        if (cur != device) cudaSetDevice(cur);
+        di = q;
     }
+    if (sm_count) *sm_count = di.sm_count;
+    if (smem_optin) *smem_optin = di.smem_optin;
+    if (smem_sm) *smem_sm = di.smem_sm;
+    if (expand_per_sm) *expand_per_sm = di.expand_per_sm;
+    return BMX_OK;
+}
+
+int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, ScanLaunch *out)
+{
+    int sm_count = 0, smem_optin = 0, smem_sm = 0;
+    if (int rc = device_info(device, &sm_count, &smem_optin, &smem_sm, nullptr)) return rc;
 
     int tile = env_int("BMX_TILE", 32768);   // profiles/tune_knobs.py: 32 KiB tiles, 2 CTAs/SM, 3 stages
     if (tile != 16384 && tile != 32768) tile = 32768;
@@ -1221,21 +1271,15 @@ int launch_scan(const ScanArgs &a, const ScanLaunch &l, bool positions, void *st
 int launch_emit(const ScanArgs &a, void *stream)
 {
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e;
-    static int sms_cache[64];
-    int dev = 0;
+    int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
-    int &sms = sms_cache[dev & 63];
-    if (sms == 0 && cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    if (int rc = device_info(dev, &sms, nullptr, nullptr, &per_sm)) return rc;
     // one resident wave of CTAs (a second wave would repeat the whole load-latency chain)
-    static int per_sm = 0;
-    if (per_sm == 0 && (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, expand_kernel, kExpandThreads, 0) != cudaSuccess || per_sm < 1))
-        per_sm = 2;
     const uint32_t items = a.num_blocks * kExpandSplit;
     uint32_t grid = std::min<uint32_t>((items + kExpandWarps - 1) / kExpandWarps, (uint32_t)(sms * per_sm));
     grid = std::max<uint32_t>(1u, std::min<uint32_t>(grid, (uint32_t)env_int("BMX_EXPAND_GRID", 1 << 30)));  // test knob
     expand_kernel<<<grid, kExpandThreads, 0, st>>>(a);
-    e = cudaGetLastError();
+    const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(BMX_E_CUDA, "expand launch: %s", cudaGetErrorString(e));
     return BMX_OK;
 }

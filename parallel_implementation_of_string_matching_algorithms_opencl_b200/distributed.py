@@ -6,11 +6,17 @@ straddle a seam (BoyreMoore.cpp:119-141).  Here rank r owns the m
 positions [lo_r, hi_r) and reads (m-1) bytes of halo behind hi_r, so every occurrence is reported
 exactly once by the rank that owns its start, with its global offset (pos_base = lo_r).
 
-Exchange step (the only collective on the path): ONE all_gather carrying each rank's count and
-(the head of) its position list; every rank sums the counts, rank 0 concatenates the lists in
-rank order, which is already globally ascending.  Longer lists send their tail to rank 0
-point-to-point.  Over NCCL this runs on NVLink/NVSwitch; the same
-code runs over gloo on CPU tensors in the tests.
+Exchange step (the only exchange on the path), two implementations:
+
+  PeerExchange   (default on GPUs) -- the library's own exchange (bmx_exchange_*, csrc/bmx_exchange.cu): every
+                 rank stores {count, head of its list} straight into its peers' mailboxes over NVLink (cudaIpc
+                 mappings between the processes), a collect kernel sums the counts and concatenates the lists on
+                 rank 0.  Two tiny kernels per step on the scan's own stream, no host synchronisation, no
+                 collective kernel waiting for SMs behind the persistent scan grid.  torch.distributed is used
+                 once, at set-up, to pass the 64-byte IPC handles around.
+  combine_hits   ONE all_gather (NCCL on GPUs, gloo in the CPU tests) carrying each rank's count and (the head
+                 of) its position list; every rank sums the counts, rank 0 concatenates the lists in rank order,
+                 which is already globally ascending.  Longer lists send their tail to rank 0 point-to-point.
 """
 from __future__ import annotations
 
@@ -31,6 +37,84 @@ def shard_bounds(n_total: int, world: int, rank: int) -> tuple[int, int]:
 def shard_read_range(n_total: int, m: int, lo: int, hi: int) -> tuple[int, int]:
     """Bytes [lo, end) a rank must hold: its own range plus the (m-1)-byte halo."""
     return lo, min(n_total, hi + max(m - 1, 0))
+
+
+def bind_to_device_numa(device_index: int):
+    """Pins the calling process (and the threads it starts later: the library's staging threads) to the CPUs
+    of the NUMA node the GPU's PCIe root hangs off, so that pinned host buffers (first touch) and the
+    pageable->pinned staging copies stay on the GPU's side of the socket interconnect.  Returns the node, or
+    None when the topology is not visible (then nothing is changed)."""
+    import os
+
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(device_index)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+class PeerExchange:
+    """One process per GPU: this rank's bmx_exchange wired to its peers through cudaIpc handles that travel
+    in one all_gather at set-up.  Every phase ends with an agreement so that a rank that cannot take part
+    (no peer access, IPC refused) fails the set-up on ALL ranks instead of leaving the others hanging."""
+
+    def __init__(self, device, group=None, dst: int = 0, head_cap: int = 4096, tail_cap: int = 0, depth: int = 4):
+        import torch
+        import torch.distributed as dist
+
+        from .host import Exchange
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+        def agree(ok: bool, what: str, err):
+            flag = torch.tensor([1 if ok else 0], device=device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+            if not int(flag.item()):
+                raise RuntimeError(f"peer exchange: {what} failed on some rank" + (f" (here: {err})" if err else ""))
+
+        self.x, err = None, None
+        try:
+            self.x = Exchange(device.index, rank, world, dst, head_cap, tail_cap, depth)
+            handle = self.x.handle()
+        except Exception as e:   # noqa: BLE001 -- reported through agree()
+            err, handle = e, bytes(Exchange.HANDLE_BYTES)
+        agree(err is None, "creating the mailbox", err)
+        mine = torch.frombuffer(bytearray(handle), dtype=torch.uint8).to(device)
+        everyone = torch.empty(world * Exchange.HANDLE_BYTES, dtype=torch.uint8, device=device)
+        dist.all_gather_into_tensor(everyone, mine, group=group)
+        try:
+            self.x.connect(everyone.cpu().numpy().tobytes())
+        except Exception as e:   # noqa: BLE001
+            err = e
+        agree(err is None, "mapping the peers' mailboxes", err)
+        self.rank, self.world, self.dst = rank, world, dst
+
+    def post(self, scanner, stream=0) -> int:
+        return self.x.post(scanner, stream)
+
+    def collect(self, out=None, stream=0) -> int:
+        return self.x.collect(out, stream)
+
+    def wait(self, seq: int):
+        return self.x.wait(seq)
+
+    def close(self):
+        if self.x is not None:
+            self.x.close()
+            self.x = None
 
 
 class PendingExchange:

@@ -95,19 +95,29 @@ def search(text, pattern, max_positions: int | None = None, variant="auto", devi
     lib = _lib.load()
     pat = _as_bytes(pattern)
     ptr, n, keep = _host_text(text)
-    if max_positions is None:
-        max_positions = max(n - len(pat) + 1, 0)
-    pos = np.empty(max_positions, dtype=np.int64)
-    count = c_uint64(0)
-    stats = BmxStats()
     if device is None:
         import torch
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-    check(lib.bmx_search_ex(device, ptr, n, pat, len(pat), pos.ctypes.data if max_positions else None,
-                            max_positions, ctypes.byref(count), _variant(variant), ctypes.byref(stats)))
+    count = c_uint64(0)
+    stats = BmxStats()
+    # "room for all" does not mean 8 bytes per text byte: start with one hit per 64 bytes and, for the rare text
+    # that is denser, fetch again with room for the count the first call reported
+    open_ended = max_positions is None
+    cap = _first_cap(n, len(pat)) if open_ended else int(max_positions)
+    while True:
+        pos = np.empty(cap, dtype=np.int64)
+        check(lib.bmx_search_ex(device, ptr, n, pat, len(pat), pos.ctypes.data if cap else None,
+                                cap, ctypes.byref(count), _variant(variant), ctypes.byref(stats)))
+        if not open_ended or count.value <= cap:
+            break
+        cap = int(count.value)
     del keep
-    out = pos[: min(count.value, max_positions)]
+    out = pos[: min(count.value, cap)]
     return (count.value, out, stats.as_dict()) if return_stats else (count.value, out)
+
+
+def _first_cap(n: int, m: int) -> int:
+    return max(0, min(n - m + 1, max(1 << 20, n // 64)))
 
 
 def search_device(text, pattern, pos_out=None, max_positions: int | None = None, pos_base: int = 0,
@@ -148,17 +158,21 @@ def search_multi(text, patterns, max_positions: int | None = None, device: int |
     pats = [_as_bytes(p) for p in patterns]
     ptr, n, keep = _host_text(text)
     k = len(pats)
-    caps = [max(n - len(p) + 1, 0) if max_positions is None else int(max_positions) for p in pats]
-    bufs = [np.empty(cap, dtype=np.int64) for cap in caps]
+    caps = [_first_cap(n, len(p)) if max_positions is None else int(max_positions) for p in pats]
     c_pats = (ctypes.c_char_p * k)(*pats)
     c_ms = (c_int32 * k)(*[len(p) for p in pats])
-    c_pos = (c_void_p * k)(*[b.ctypes.data if b.size else None for b in bufs])
-    c_caps = (c_int64 * k)(*caps)
     counts = (c_uint64 * k)()
     if device is None:
         import torch
         device = torch.cuda.current_device() if torch.cuda.is_available() else 0
-    check(lib.bmx_search_multi(device, ptr, n, k, c_pats, c_ms, c_pos, c_caps, counts))
+    while True:
+        bufs = [np.empty(cap, dtype=np.int64) for cap in caps]
+        c_pos = (c_void_p * k)(*[b.ctypes.data if b.size else None for b in bufs])
+        c_caps = (c_int64 * k)(*caps)
+        check(lib.bmx_search_multi(device, ptr, n, k, c_pats, c_ms, c_pos, c_caps, counts))
+        if max_positions is not None or all(int(counts[i]) <= caps[i] for i in range(k)):
+            break
+        caps = [max(caps[i], int(counts[i])) for i in range(k)]      # a pattern denser than one hit per 64 bytes
     del keep
     return [(int(counts[i]), bufs[i][: min(int(counts[i]), caps[i])]) for i in range(k)]
 
@@ -259,6 +273,68 @@ class Scanner:
         return count.value, stats.as_dict()
 
 
+class Exchange:
+    """The exchange step of the sharded scan over NVLink peer memory (bmx_exchange_*): one per rank (= GPU).
+
+    post(scanner) ships the scanner's running result {count, list} as the next step, collect() completes the
+    oldest uncollected step (rank dst also concatenates the lists into `out`), wait(seq) blocks the host until
+    that step has been collected here and returns (total, per-rank counts, gathered length).  post/collect only
+    enqueue a kernel; nothing synchronises with the host except wait().
+    """
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, device: int, rank: int, world: int, dst: int = 0, head_cap: int = 4096, tail_cap: int = 0, depth: int = 4):
+        self._lib = _lib.load()
+        self._h = c_void_p()
+        self.rank, self.world, self.dst = rank, world, dst
+        check(self._lib.bmx_exchange_create(device, rank, world, dst, head_cap, tail_cap, depth, ctypes.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            self._lib.bmx_exchange_destroy(self._h)
+            self._h = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(self.HANDLE_BYTES)
+        check(self._lib.bmx_exchange_handle(self._h, buf))
+        return buf.raw
+
+    def connect(self, handles: bytes):
+        """handles: world x 64 bytes in rank order (this rank's own entry is ignored)."""
+        assert len(handles) == self.world * self.HANDLE_BYTES
+        check(self._lib.bmx_exchange_connect(self._h, handles))
+
+    @staticmethod
+    def connect_local(exchanges):
+        """All ranks live in this process: wire them up directly (peer access is enabled as needed)."""
+        arr = (c_void_p * len(exchanges))(*[x._h for x in exchanges])
+        check(_lib.load().bmx_exchange_connect_local(arr, len(exchanges)))
+
+    def post(self, scanner, stream=0) -> int:
+        seq = c_uint64(0)
+        check(self._lib.bmx_exchange_post(self._h, scanner._h, c_void_p(stream), ctypes.byref(seq)))
+        return seq.value
+
+    def collect(self, out=None, stream=0) -> int:
+        seq = c_uint64(0)
+        cap = 0 if out is None else out.numel()
+        check(self._lib.bmx_exchange_collect(self._h, c_void_p(out.data_ptr()) if cap else None, cap, c_void_p(stream), ctypes.byref(seq)))
+        return seq.value
+
+    def wait(self, seq: int):
+        total, gathered = c_uint64(0), c_int64(0)
+        counts = (c_uint64 * self.world)()
+        check(self._lib.bmx_exchange_wait(self._h, seq, ctypes.byref(total), counts, ctypes.byref(gathered)))
+        return total.value, [int(c) for c in counts], gathered.value
+
+
 class MultiGpu:
     """Single-process multi-GPU search over host text (bmx_mg_*): shards + (m-1) halo, one host thread per GPU."""
 
@@ -283,12 +359,33 @@ class MultiGpu:
         """(count, positions, per_gpu_counts) -- the serial-reference result, like search()."""
         pat = _as_bytes(pattern)
         ptr, n, keep = _host_text(text)
-        if max_positions is None:
-            max_positions = max(n - len(pat) + 1, 0)
-        pos = np.empty(max_positions, dtype=np.int64)
+        open_ended = max_positions is None
+        cap = _first_cap(n, len(pat)) if open_ended else int(max_positions)
         count = c_uint64(0)
         shard = (c_uint64 * self.ngpus)()
-        check(self._lib.bmx_mg_search(self._h, ptr, n, pat, len(pat), pos.ctypes.data if max_positions else None,
-                                      max_positions, ctypes.byref(count), shard))
+        while True:
+            pos = np.empty(cap, dtype=np.int64)
+            check(self._lib.bmx_mg_search(self._h, ptr, n, pat, len(pat), pos.ctypes.data if cap else None,
+                                          cap, ctypes.byref(count), shard))
+            if not open_ended or count.value <= cap:
+                break
+            cap = int(count.value)
         del keep
-        return count.value, pos[: min(count.value, max_positions)], [int(x) for x in shard]
+        return count.value, pos[: min(count.value, cap)], [int(x) for x in shard]
+
+    def search_device(self, shards, pos_bases, pattern, pos_out=None):
+        """Device-resident shards (CUDA uint8 tensors, shard r on GPU r, own range + (m-1)-byte halo) ->
+        (count, positions on GPU 0 or None, per_gpu_counts); the exchange step runs inside the library over
+        peer memory (bmx_mg_search_device)."""
+        pat = _as_bytes(pattern)
+        assert len(shards) == self.ngpus == len(pos_bases)
+        ptrs = (c_void_p * self.ngpus)(*[t.data_ptr() if t.numel() else None for t in shards])
+        ns = (c_int64 * self.ngpus)(*[t.numel() for t in shards])
+        bases = (c_int64 * self.ngpus)(*[int(b) for b in pos_bases])
+        cap = 0 if pos_out is None else pos_out.numel()
+        count = c_uint64(0)
+        shard = (c_uint64 * self.ngpus)()
+        check(self._lib.bmx_mg_search_device(self._h, ptrs, ns, bases, pat, len(pat), c_void_p(pos_out.data_ptr()) if cap else None,
+                                             cap, ctypes.byref(count), shard))
+        found = None if pos_out is None else pos_out[: min(count.value, cap)]
+        return count.value, found, [int(x) for x in shard]

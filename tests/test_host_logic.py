@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol(bmx):
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in include/bmx.h but not exported"
     assert declared == set(bmx._lib.EXPORTS)
-    assert bmx.version() == 100
+    assert bmx.version() == 200
 
 
 def test_tables_equal_reference_tables(bmx, golden):

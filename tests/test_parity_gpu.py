@@ -35,6 +35,15 @@ def to_dev(buf, dev, misalign: int = 0):
     return view
 
 
+def _find_all(text: bytes, pat: bytes) -> np.ndarray:
+    """All (overlapping) occurrences with bytes.find -- for patterns too long for the oracle's O(m^3) tables."""
+    out, i = [], text.find(pat)
+    while i >= 0:
+        out.append(i)
+        i = text.find(pat, i + 1)
+    return np.array(out, dtype=np.int64)
+
+
 def gpu_positions(bmx, text_dev, pat, variant="auto", cap=None):
     n = text_dev.numel()
     cap = max(n - len(pat) + 1, 1) if cap is None else cap
@@ -369,12 +378,12 @@ def test_find_first_equals_first_position_of_the_serial_result(bmx, oracle, dev,
         want_list = oracle.search(text, pat)
         want = int(want_list[0]) if want_list.size else -1
         assert want == text.find(pat)
-        for kb in ("1", "7", None):
+        for kb in ("1", "7", None):          # host flavour: tiny H2D chunks force many chained find-first scans
             if kb is None:
-                monkeypatch.delenv("BMX_FIND_CHUNK_KB", raising=False)
+                monkeypatch.delenv("BMX_H2D_CHUNK_KB", raising=False)
                 monkeypatch.delenv("BMX_H2D_CHUNK_MB", raising=False)
             else:
-                monkeypatch.setenv("BMX_FIND_CHUNK_KB", kb)
+                monkeypatch.setenv("BMX_H2D_CHUNK_KB", kb)
             td = to_dev(text, dev, misalign=rnd.randint(0, 17))
             assert bmx.find_first_device(td, pat) == want, (it, n, m, mode, kb, "device")
             assert bmx.find_first(text, pat) == want, (it, n, m, mode, kb, "host")
@@ -390,6 +399,110 @@ def test_find_first_equals_first_position_of_the_serial_result(bmx, oracle, dev,
         assert bmx.find_first_device(to_dev(t, dev), pat) == at
     with pytest.raises(bmx.BmxError):
         bmx.find_first(b"abc", b"")
+    # many matches spread over many tiles and CTAs: the device-side stop must still return the SMALLEST start
+    monkeypatch.delenv("BMX_H2D_CHUNK_MB", raising=False)
+    for seed, alphabet, m in ((3, "dna", 7), (4, "dna", 11), (5, "ascii95", 2)):
+        t = bmx.synth.fill_host(0, 40 << 20, seed, bmx.synth.ALPHABETS[alphabet])
+        for at in (39 << 20, 17 << 20, 5_000_001, 123_456, 0):
+            pat = t[at:at + m].tobytes()
+            want = t.tobytes().find(pat)
+            td = to_dev(t, dev)
+            for _ in range(3):       # repeated searches: the epoch-tagged key word is never cleared in between
+                assert bmx.find_first_device(td, pat) == want
+            assert bmx.find_first(t, pat) == want
+
+
+def test_host_path_ring_layout_and_growing_position_buffer(bmx, oracle, monkeypatch):
+    """Host text that "does not fit" (BMX_RESIDENT_MAX_MB=0): four ring slots of 64 KiB, the previous chunk's last
+    m-1 bytes carried in front of every chunk.  Plus the position buffer that starts small and follows the count."""
+    rnd = random.Random(77)
+    base = bmx.synth.fill_host(0, (1 << 20) + 12345, 5, bmx.synth.ALPHABETS["dna"])
+    for layout in ("ring", "resident"):
+        if layout == "ring":
+            monkeypatch.setenv("BMX_RESIDENT_MAX_MB", "0")
+            monkeypatch.setenv("BMX_H2D_CHUNK_KB", "64")
+        else:
+            monkeypatch.delenv("BMX_RESIDENT_MAX_MB", raising=False)
+            monkeypatch.setenv("BMX_H2D_CHUNK_KB", "256")
+        for m in (1, 3, 14, 200, 5000):
+            text = base.copy()
+            at = (64 << 10) * rnd.randint(1, 10) - rnd.randint(0, m)        # straddles (or touches) a chunk seam
+            pat = text[at:at + m].tobytes()
+            for seam in range(1, 12):
+                text[(seam << 16) - m // 2:(seam << 16) - m // 2 + m] = np.frombuffer(pat, dtype=np.uint8)
+            want = oracle.search(text.tobytes(), pat) if m < 2000 else _find_all(text.tobytes(), pat)
+            for src in (text, torch.from_numpy(text.copy()).pin_memory()):
+                count, got = bmx.search(src, pat)
+                assert count == want.size and np.array_equal(got, want), (layout, m)
+                count, got = bmx.search(src, pat, max_positions=0)
+                assert count == want.size
+                count, got = bmx.search(src, pat, max_positions=5)
+                assert count == want.size and np.array_equal(got, want[:5])
+                assert bmx.find_first(src, pat) == (int(want[0]) if want.size else -1)
+        # K patterns: the ring layout ingests the text once per pattern, the resident one once
+        pats = [base[100:109].tobytes(), b"ACGTACGTAC", base[70000:70003].tobytes()]
+        res = bmx.search_multi(base, pats)
+        for (count, got), p in zip(res, pats):
+            want = oracle.search(base.tobytes(), p)
+            assert count == want.size and np.array_equal(got, want)
+        # denser than the first guess of the position buffer (1 Mi entries): the buffer follows the count
+        dense = np.full(3_000_000, ord("a"), dtype=np.uint8)
+        dense[1_234_567] = ord("b")
+        count, got = bmx.search(dense, b"aa")
+        want = oracle.search(dense.tobytes(), b"aa")
+        assert count == want.size and np.array_equal(got, want)
+        count, got = bmx.search(dense, b"aa", max_positions=2_000_000)
+        assert count == want.size and np.array_equal(got, want[:2_000_000])
+        assert bmx._lib.load().bmx_release_memory(-1) == 0
+
+
+def test_cached_buffers_threads_and_release(bmx, oracle, dev):
+    """Threads come and go (each owns its cached buffers and gives them back when it exits), bmx_release_memory
+    empties the caller's cache, and the next call simply allocates again."""
+    import threading
+    text = bmx.synth.fill_host(0, 3 << 20, 8, bmx.synth.ALPHABETS["ascii95"])
+    pat = text[99_000:99_012].tobytes()
+    want = oracle.search(text.tobytes(), pat)
+    free0 = torch.cuda.mem_get_info()[0]
+    errs = []
+
+    def work():
+        try:
+            for _ in range(3):
+                count, got = bmx.search(text, pat)
+                assert count == want.size and np.array_equal(got, want)
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    for _ in range(6):
+        ts = [threading.Thread(target=work) for _ in range(3)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+    assert not errs, errs
+    count, got = bmx.search(text, pat)
+    assert count == want.size
+    assert bmx._lib.load().bmx_release_memory(-1) == 0
+    torch.cuda.synchronize()
+    free1 = torch.cuda.mem_get_info()[0]
+    assert free0 - free1 < (64 << 20), "exited threads and bmx_release_memory must give device memory back"
+    count, got = bmx.search(text, pat)
+    assert count == want.size and np.array_equal(got, want)
+
+
+def test_pattern_cache_across_streams_and_patterns(bmx, oracle, dev):
+    """bmx_search_device skips the pattern upload when the pattern is unchanged; another stream must still see it."""
+    text = bmx.synth.fill_host(0, 2 << 20, 12, bmx.synth.ALPHABETS["dna"])
+    td = to_dev(text.tobytes(), dev)
+    pats = [text[5000:5012].tobytes(), text[77:85].tobytes(), b"ACGT"]
+    wants = [oracle.search(text.tobytes(), p) for p in pats]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream(), None]
+    rnd = random.Random(6)
+    for it in range(60):
+        k = rnd.randrange(3) if it % 3 else 0           # mostly the same pattern again
+        st = streams[rnd.randrange(3)]
+        count, got, _ = bmx.search_device(td, pats[k], max_positions=wants[k].size + 3, stream=st)
+        (st or torch.cuda.current_stream()).synchronize()
+        assert count == wants[k].size and np.array_equal(got.cpu().numpy(), wants[k]), (it, k)
 
 
 def test_search_multi_shares_one_ingest(bmx, oracle, monkeypatch):
