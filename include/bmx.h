@@ -252,12 +252,12 @@ int bmx_mg_search(bmx_mg *mg, const char *text, int64_t n, const char *pat, int3
  * process per GPU (torchrun): each rank publishes bmx_exchange_handle (a cudaIpcMemHandle, 64 bytes), the
  * handles travel by any means (distributed.py uses one torch.distributed all_gather at set-up) and
  * bmx_exchange_connect maps them.  head_cap positions per rank ride along with the header (ring of `depth`
- * steps); longer lists use the single-buffered tail area (tail_cap positions per source, on dst only).  The
+ * steps); longer lists use the tail areas (two of tail_cap positions per source, alternating, on dst only).  The
  * gathered list is always a prefix of the global ascending list: it ends behind the first rank whose list did
  * not fit (its own pos_cap, or head_cap + tail_cap); the total count is exact regardless.
  *
  * Call order per rank and step: bmx_scanner_begin/scan ... -> bmx_exchange_post -> (later) bmx_exchange_collect;
- * at most depth-1 steps may be posted and not yet collected.  Collecting step q-1 after posting step q keeps
+ * at most depth-1 steps (with tail_cap > 0: at most 2) may be posted and not yet collected.  Collecting step q-1 after posting step q keeps
  * every GPU from ever waiting for a peer.  Device-side waits time out after BMX_XCHG_TIMEOUT_MS (default
  * 20000) and surface as BMX_E_EXCHANGE from bmx_exchange_wait.  All ranks must be connected before the first
  * post and idle before any rank is destroyed (a barrier of the caller's choice).

@@ -11,7 +11,7 @@
 //            slot [q % depth][r] of EVERY rank and the first head_cap positions into rank dst's mailbox, through
 //            peer pointers (NVLink P2P stores; cudaIpc mappings when the ranks are processes), then publishes
 //            the step number with st.release.sys.  Lists longer than head_cap (dense texts) put their tail into
-//            the per-source tail area of dst.
+//            the per-source tail areas of dst (two per source, alternating).
 //   collect  (any later point of the same stream) waits for the world's step numbers with ld.acquire.sys, sums
 //            the counts, concatenates the lists on dst, writes {total, per-rank counts, list length} into a
 //            host-mapped result ring and returns one credit (ack) to every source, which is what lets a source
@@ -40,6 +40,7 @@ constexpr int kMaxRanks = 16;
 constexpr int kXchgThreads = 256;
 constexpr int kTailBlocks = 32;      // blocks of the post kernel that ship a list's tail
 constexpr int kCollectBlocks = 16;   // blocks of the collect kernel on dst
+constexpr unsigned long long kTailDepth = 2;   // tail areas per source on dst
 
 struct XHdr {  // one per (slot, source) in every mailbox; seq is stored last (release)
     unsigned long long seq, count, held, sent;
@@ -116,17 +117,17 @@ __device__ __forceinline__ unsigned long long *x_ack(unsigned char *mb, const XA
 {
     return reinterpret_cast<unsigned long long *>(mb + A.off_ack);
 }
-__device__ __forceinline__ unsigned long long *x_tdone(unsigned char *mb, const XArgs &A)
+__device__ __forceinline__ unsigned long long *x_tdone(unsigned char *mb, const XArgs &A, uint32_t tslot)
 {
-    return reinterpret_cast<unsigned long long *>(mb + A.off_tdone);
+    return reinterpret_cast<unsigned long long *>(mb + A.off_tdone) + (size_t)tslot * A.world;
 }
 __device__ __forceinline__ int64_t *x_head(unsigned char *mb, const XArgs &A, uint32_t slot, int src)
 {
     return reinterpret_cast<int64_t *>(mb + A.off_head) + ((size_t)slot * A.world + src) * (size_t)A.head_cap;
 }
-__device__ __forceinline__ int64_t *x_tail(unsigned char *mb, const XArgs &A, int src)
+__device__ __forceinline__ int64_t *x_tail(unsigned char *mb, const XArgs &A, uint32_t tslot, int src)
 {
-    return reinterpret_cast<int64_t *>(mb + A.off_tail) + (size_t)src * (size_t)A.tail_cap;
+    return reinterpret_cast<int64_t *>(mb + A.off_tail) + ((size_t)tslot * A.world + src) * (size_t)A.tail_cap;
 }
 
 // Block 0: credit check, head of the list -> dst, header -> everyone.  Blocks 1..: tail of a long list -> dst.
@@ -162,12 +163,14 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_post_kernel(const __grid_co
         return;
     }
     if (sent <= A.head_cap) return;
-    // the tail area of dst is single-buffered: dst must have consumed the previous step
+    // the tail area of dst is double-buffered (kTailDepth): dst must have consumed the step before the previous one.
+    // (Single buffering would deadlock a caller that collects step q-1 BEHIND post q on dst's own stream.)
     __shared__ int s_good;
-    if (tid == 0) s_good = A.seq <= 1 || spin_until_ge(x_ack(me, A) + A.dst, A.seq - 1, A.timeout_ns) ? 1 : 0;
+    const uint32_t tslot = (uint32_t)(A.seq % kTailDepth);
+    if (tid == 0) s_good = A.seq <= kTailDepth || spin_until_ge(x_ack(me, A) + A.dst, A.seq - kTailDepth, A.timeout_ns) ? 1 : 0;
     __syncthreads();
     if (!s_good && tid == 0) atomicOr(A.local + 2, 2u);
-    int64_t *tl = x_tail(A.mb[A.dst], A, A.rank);
+    int64_t *tl = x_tail(A.mb[A.dst], A, tslot, A.rank);
     const long long n_tail = sent - A.head_cap;
     const long long stride = (long long)(gridDim.x - 1) * kXchgThreads;
     for (long long i = (long long)(blockIdx.x - 1) * kXchgThreads + tid; i < n_tail; i += stride) tl[i] = A.pos[A.head_cap + i];
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_post_kernel(const __grid_co
     if (tid == 0 && atomicAdd(A.local + 0, 1u) == gridDim.x - 2) {  // the last tail block publishes
         A.local[0] = 0u;
         __threadfence_system();
-        st_release_sys(x_tdone(A.mb[A.dst], A) + A.rank, A.seq);
+        st_release_sys(x_tdone(A.mb[A.dst], A, tslot) + A.rank, A.seq);
     }
 }
 
@@ -199,7 +202,8 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_collect_kernel(const __grid
         good = spin_until_ge(&h->seq, A.seq, A.timeout_ns);
         s_count[tid] = ld_relaxed_sys(&h->count);
         s_sent[tid] = ld_relaxed_sys(&h->sent);
-        if (gather && (long long)s_sent[tid] > A.head_cap) good = good && spin_until_ge(x_tdone(me, A) + tid, A.seq, A.timeout_ns);
+        if (gather && (long long)s_sent[tid] > A.head_cap)
+            good = good && spin_until_ge(x_tdone(me, A, (uint32_t)(A.seq % kTailDepth)) + tid, A.seq, A.timeout_ns);
     }
     if (!__syncthreads_and(good) && tid == 0) atomicOr(A.local + 2, 4u);
     if (tid == 0) {
@@ -221,7 +225,7 @@ __global__ void __launch_bounds__(kXchgThreads) xchg_collect_kernel(const __grid
         const long long stride = (long long)gridDim.x * kXchgThreads;
         for (int r = 0; r < A.world; ++r) {
             const long long take = (long long)s_take[r], base = (long long)s_off[r];
-            const int64_t *hd = x_head(me, A, slot, r), *tl = x_tail(me, A, r);
+            const int64_t *hd = x_head(me, A, slot, r), *tl = x_tail(me, A, (uint32_t)(A.seq % kTailDepth), r);
             for (long long i = (long long)blockIdx.x * kXchgThreads + tid; i < take && base + i < A.out_cap; i += stride)
                 A.out[base + i] = __ldcv(i < A.head_cap ? hd + i : tl + (i - A.head_cap));  // written by a peer: bypass L1
         }
@@ -328,9 +332,9 @@ int bmx_exchange_create(int device, int rank, int world, int dst, int64_t head_c
     auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
     x->off_ack = align(sizeof(XHdr) * (size_t)depth * world);
     x->off_tdone = x->off_ack + align(8 * (size_t)world);
-    x->off_head = x->off_tdone + align(8 * (size_t)world);
+    x->off_head = x->off_tdone + align(8 * (size_t)world * kTailDepth);
     x->off_tail = x->off_head + align(8 * (size_t)depth * world * (size_t)head_cap);
-    x->bytes = rank == dst ? x->off_tail + align(8 * (size_t)world * (size_t)tail_cap) : x->off_head;
+    x->bytes = rank == dst ? x->off_tail + align(8 * (size_t)world * (size_t)tail_cap * kTailDepth) : x->off_head;
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&x->mailbox), x->bytes);  // plain cudaMalloc: IPC-exportable
     if (e == cudaSuccess) e = cudaMemset(x->mailbox, 0, std::min(x->bytes, x->off_head));
     if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void **>(&x->d_local), 64);
@@ -438,6 +442,8 @@ int bmx_exchange_post(bmx_exchange *x, bmx_scanner *s, void *stream, uint64_t *s
     if (x->posted - x->collected >= (uint64_t)x->depth - 1)
         return fail(BMX_E_BADARG, "bmx_exchange_post: %llu steps posted but not collected (depth %d)",
                     (unsigned long long)(x->posted - x->collected), x->depth);
+    if (x->tail_cap > 0 && x->posted - x->collected >= kTailDepth)
+        return fail(BMX_E_BADARG, "bmx_exchange_post: with a tail area at most %d steps may be posted and not collected", (int)kTailDepth);
     BMX_CUDA(cudaSetDevice(x->device));
     XArgs a = make_args(x, x->posted + 1);
     a.count = result_slot(s);
