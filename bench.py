@@ -187,12 +187,13 @@ def oracle_search(arr, pat, want_positions: bool, threads: int = -1, cap_hint: i
     return int(cnt.value), (pos[: min(int(cnt.value), cap)] if want_positions else None), kind
 
 
-def oracle_verdict(torch, text, lo, pat, count, pos, cap, dense):
+def oracle_verdict(torch, text, lo, pat, count, pos, cap, dense, host=None):
     """The CUDA result against the oracle on the same bytes (outside every timed region): the shard goes back
     to the host, the reference's serial code (windowed over all host threads) scans it, and count + position
     list must be identical.  Dense texts (a list of ~n positions would need 8n bytes of host memory) compare
     the count with the oracle's and the list with its closed form on the device."""
-    host = text.cpu().numpy()
+    if host is None:
+        host = text.cpu().numpy()
     if dense:
         ocount, _, kind = oracle_search(host, pat, False)
         k = min(count, cap)
@@ -443,8 +444,13 @@ def run_ours(args):
     # serial code on the same shard; rank 0's gathered list against the rank-ordered concatenation of the oracle lists
     verified_by = "not run (--no-verify)"
     oracle_hits = None
+    host_text = None
+    if not (args.no_verify and args.no_e2e):     # one pinned host copy of the shard serves the oracle and the e2e leg
+        host_text = torch.empty(end - lo, dtype=torch.uint8, pin_memory=True)
+        host_text.copy_(text)
+        torch.cuda.synchronize()
     if not args.no_verify:
-        ok_local, verified_by, ocount, opos = oracle_verdict(torch, text, lo, pat, count, pos, cap, dense)
+        ok_local, verified_by, ocount, opos = oracle_verdict(torch, text, lo, pat, count, pos, cap, dense, host=host_text.numpy())
         ok = ok and ok_local
         oracle_hits = ocount
         if world > 1:
@@ -465,9 +471,6 @@ def run_ours(args):
     e2e = e2e_pageable = None
     host_sample = None
     if not args.no_e2e:
-        host_text = torch.empty(end - lo, dtype=torch.uint8, pin_memory=True)
-        host_text.copy_(text)
-        torch.cuda.synchronize()
         e2e_cap = min(cap, 1 << 24)
         e2e_steps = max(2, min(args.steps, args.e2e_steps))
 

@@ -125,14 +125,24 @@ int bmx_search_device(const void *d_text, int64_t n, const char *pat, int32_t m,
                       float *device_ms, void *stream);
 
 /*
- * K patterns over one host text (multi-pattern batching; the reference builds its tables once per
- * pattern, BoyreMoore.cpp:150-190, and would re-send the text for each).  The text is copied to the device
- * ONCE, overlapped with the scan for pats[0]; every further pattern scans the resident copy.  Per pattern k:
- * counts[k] and, when pos_out && pos_out[k], the first min(counts[k], pos_cap[k]) ascending positions --
- * exactly what bmx_search_ex returns for that pattern alone.  A pattern longer than the text counts 0.
+ * K patterns, ONE pass over the text (multi-pattern batching; the reference builds its tables once per
+ * pattern, BoyreMoore.cpp:150-190, and would read -- and re-send -- the text for each).  All patterns share one
+ * candidate table in shared memory (a bitmap over the hash of an aligned q-gram, probed once per aligned text word
+ * whatever K is; flagged words go on to an exact table and a comparison with the pattern they name), every match
+ * bumps its pattern's counter, the union of all matches goes through the ordinary ordered emission and one CTA per
+ * pattern splits it into K ascending lists.  Per pattern k: counts[k] (always exact) and, when pos_out &&
+ * pos_out[k], the first min(counts[k], pos_cap[k]) ascending positions -- exactly what bmx_search_ex /
+ * bmx_search_device returns for that pattern alone.  A pattern longer than the text counts 0.
+ * Eligible for the single pass: 1 <= npat <= 64 and every pattern 7 <= m <= 4096 bytes; other sets are searched
+ * pattern by pattern over the same device copy (same results).
+ * bmx_search_multi: host text, copied to the device ONCE (chunked; a text larger than the device streams through
+ * the ring once per pattern).  bmx_search_multi_device: d_text and the d_pos_out[k] are DEVICE pointers on the
+ * current device, pats / ms / pos_cap / counts and the array d_pos_out itself are host memory; synchronous on `stream`.
  */
 int bmx_search_multi(int device, const char *text, int64_t n, int32_t npat, const char *const *pats,
                      const int32_t *ms, int64_t *const *pos_out, const int64_t *pos_cap, uint64_t *counts);
+int bmx_search_multi_device(const void *d_text, int64_t n, int32_t npat, const char *const *pats, const int32_t *ms,
+                            int64_t *const *d_pos_out, const int64_t *pos_cap, uint64_t *counts, void *stream);
 
 /*
  * First occurrence with early exit -- the query of the vendored CUDA sample

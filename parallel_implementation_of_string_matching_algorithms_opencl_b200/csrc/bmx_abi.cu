@@ -146,6 +146,7 @@ int bmx_scanner_set_pattern(bmx_scanner *s, const char *pat, int32_t m, int32_t 
         return BMX_OK;
     }
     s->m = m;
+    s->m_halo = 0;
     s->requested_variant = variant;
     s->qgram_knob = knob;
     s->variant = resolve_variant(variant, m);
@@ -228,7 +229,7 @@ int bmx_scanner_scan(bmx_scanner *s, const void *d_text, int64_t n, int64_t pos_
     a.pos_cap = s->pos_cap;
 
     ScanLaunch launch{};
-    if (int rc = plan_scan(s->device, s->variant, s->m, s->positions, &a, &launch)) return rc;
+    if (int rc = plan_scan(s->device, s->variant, s->m_halo ? s->m_halo : s->m, s->positions, &a, &launch)) return rc;
 
     // scratch: two "zero halves" [tickets 16 B | scan count u64 + pad | block_sum u32 x blocks | seg_count u16 x segs |
     //          item_flag u8 x items], each zero whenever a scan starts on it, followed by
@@ -357,7 +358,7 @@ void ThreadCtx::release_buffers()
     if (cudaSetDevice(device) == cudaSuccess) {
         if (copy_stream) cudaStreamSynchronize(copy_stream);
         if (scan_stream) cudaStreamSynchronize(scan_stream);
-        for (DevBuf *b : {&text, &pos, &misc}) {
+        for (DevBuf *b : {&text, &pos, &misc, &aux}) {
             if (b->p) cudaFree(b->p);
             *b = DevBuf{};
         }

@@ -41,7 +41,7 @@ struct ThreadCtx {
     std::vector<cudaEvent_t> events;
     unsigned char *bounce[kBounce] = {nullptr, nullptr, nullptr};
     size_t bounce_bytes = 0;
-    DevBuf text, pos, misc;
+    DevBuf text, pos, misc, aux;
     ThreadCtx() = default;
     ThreadCtx(const ThreadCtx &) = delete;
     ThreadCtx &operator=(const ThreadCtx &) = delete;
@@ -55,5 +55,10 @@ int ensure_streams(ThreadCtx &c, int device, size_t nevents);
 // Grows b to at least `bytes` (never shrinks).  The old block may still be in use by work enqueued on the
 // context's streams, so they are drained before it is freed.  NOMEM leaves b empty.
 int ensure_buf(ThreadCtx &c, DevBuf &b, size_t bytes);
+int scanner_begin_find(bmx_scanner *s, void *stream);   // find-first search: count-only kernels + early stop (bmx_abi.cu)
+// K patterns in one pass over device-resident text (bmx_multipat.cu)
+bool multi_set_eligible(int32_t npat, const int32_t *ms);
+int multi_scan_resident(ThreadCtx &c, const unsigned char *d_text, int64_t n, int32_t npat, const char *const *pats,
+                        const int32_t *ms, int64_t *const *d_out, const int64_t *caps, uint64_t *counts, cudaStream_t st);
 
 }  // namespace bmx

@@ -28,10 +28,6 @@
 
 using namespace bmx;
 
-namespace bmx {
-int scanner_begin_find(bmx_scanner *s, void *stream);  // bmx_abi.cu
-}
-
 namespace {
 
 constexpr int kRing = 4;
@@ -105,6 +101,7 @@ struct Ingest {
     int64_t want_cap = 0;        // positions the caller can use (0: count only)
     bool find_first = false;     // stop copying and scanning behind the first match
     bool need_resident = false;  // the caller wants to re-scan the device copy (bmx_search_multi)
+    bool copy_only = false;      // ingest without scanning (the caller scans the resident copy itself)
     // out
     uint64_t count = 0;
     int64_t dev_cap = 0;         // ctx.pos holds min(count, dev_cap) positions
@@ -124,6 +121,7 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
     io->resident = false;
     io->stats = bmx_stats{};
     if (n < m && !(io->need_resident && n > 0)) return BMX_OK;
+    if (io->copy_only && !io->need_resident) return fail(BMX_E_BADARG, "copy-only ingest needs the resident layout");
     BMX_CUDA(cudaSetDevice(device));
 
     int64_t chunk = std::max<long>(1, env_long("BMX_H2D_CHUNK_MB", 64)) << 20;
@@ -193,11 +191,14 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
         // the copy stream must not overwrite text that scans of an earlier call (or pass) still read
         BMX_CUDA(cudaEventRecord(c->events[ev_copy], c->scan_stream));
         BMX_CUDA(cudaStreamWaitEvent(c->copy_stream, c->events[ev_copy], 0));
-        int rc = bmx_scanner_set_pattern(c->scanner, pat, m, variant, c->scan_stream);
-        if (rc == BMX_OK)
-            rc = io->find_first ? scanner_begin_find(c->scanner, c->scan_stream)
-                                : bmx_scanner_begin(c->scanner, cap > 0 ? static_cast<int64_t *>(c->pos.p) : nullptr, cap, c->scan_stream);
-        if (rc != BMX_OK) return rc;
+        int rc = BMX_OK;
+        if (!io->copy_only) {
+            rc = bmx_scanner_set_pattern(c->scanner, pat, m, variant, c->scan_stream);
+            if (rc == BMX_OK)
+                rc = io->find_first ? scanner_begin_find(c->scanner, c->scan_stream)
+                                    : bmx_scanner_begin(c->scanner, cap > 0 ? static_cast<int64_t *>(c->pos.p) : nullptr, cap, c->scan_stream);
+            if (rc != BMX_OK) return rc;
+        }
 
         int64_t scanned = 0;  // resident layout: start positions < scanned are done
         int64_t q = 0;        // find-first: scans enqueued so far
@@ -235,7 +236,7 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
             if (resident) {
                 // every match lying fully inside the bytes copied so far, not yet reported
                 const int64_t have = off + len, span = have - scanned;
-                if (span >= m) {
+                if (span >= m && !io->copy_only) {
                     if ((rc = bmx_scanner_scan(c->scanner, d_text + scanned, span, pos_base + scanned, c->scan_stream)) != BMX_OK) return rc;
                     scanned = have - m + 1;
                     scanned_now = true;
@@ -257,6 +258,10 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
                 if (q >= 1) found = first_of(q - 1);   // one scan behind: the GPU never waits for the host
                 ++q;
             }
+        }
+        if (io->copy_only) {
+            BMX_CUDA(cudaStreamSynchronize(c->scan_stream));   // every chunk has landed (the scan stream waited for each copy)
+            return BMX_OK;
         }
         uint64_t count = 0;
         if ((rc = bmx_scanner_finish(c->scanner, &count, &io->stats, c->scan_stream)) != BMX_OK) return rc;
@@ -353,11 +358,14 @@ int bmx_search_multi(int device, const char *text, int64_t n, int32_t npat, cons
         BMX_CUDA(cudaStreamSynchronize(c->scan_stream));   // c->pos is reused by the next pattern
         return BMX_OK;
     };
-    // pattern 0 rides on the ingest
+    // the text crosses PCIe once; then all patterns in one pass over the resident copy when the set is eligible
+    // (bmx_multipat.cu), else pattern by pattern
     Ingest io;
-    io.want_cap = cap_of(0);
     io.need_resident = true;
-    int rc = ingest_and_scan(*c, device, text, n, pats[0], ms[0], 0, BMX_VARIANT_AUTO, &io);
+    io.copy_only = true;
+    int32_t m_min = ms[0];
+    for (int32_t k = 1; k < npat; ++k) m_min = std::min(m_min, ms[k]);
+    int rc = ingest_and_scan(*c, device, text, n, pats[0], m_min, 0, BMX_VARIANT_AUTO, &io);
     if (rc == BMX_E_NOMEM) {
         // larger than the device: every pattern streams the text through the ring on its own
         for (int32_t k = 0; k < npat; ++k) {
@@ -370,10 +378,43 @@ int bmx_search_multi(int device, const char *text, int64_t n, int32_t npat, cons
         return BMX_OK;
     }
     if (rc != BMX_OK) return rc;
-    counts[0] = io.count;
-    if ((rc = fetch(0, io.count, io.dev_cap)) != BMX_OK) return rc;
     const unsigned char *d_text = static_cast<const unsigned char *>(c->text.p);
-    for (int32_t k = 1; k < npat; ++k) {
+    if (multi_set_eligible(npat, ms)) {
+        // device-side output buffers: a first guess per pattern (one hit per 64 bytes), grown to the counts if a
+        // pattern turns out denser -- the resident text is simply scanned again
+        std::vector<int64_t> dev_cap((size_t)npat, 0);
+        for (int32_t k = 0; k < npat; ++k) dev_cap[(size_t)k] = first_pos_cap(n, ms[k], cap_of(k));
+        for (int pass = 0; pass < 2; ++pass) {
+            size_t total = 0;
+            for (int32_t k = 0; k < npat; ++k) total += ((size_t)dev_cap[(size_t)k] * 8 + 255) & ~size_t(255);
+            if ((rc = ensure_buf(*c, c->aux, std::max<size_t>(total, 256))) != BMX_OK) return rc;
+            std::vector<int64_t *> outs((size_t)npat, nullptr);
+            size_t at = 0;
+            for (int32_t k = 0; k < npat; ++k) {
+                if (dev_cap[(size_t)k] > 0) outs[(size_t)k] = reinterpret_cast<int64_t *>(static_cast<unsigned char *>(c->aux.p) + at);
+                at += ((size_t)dev_cap[(size_t)k] * 8 + 255) & ~size_t(255);
+            }
+            if ((rc = multi_scan_resident(*c, d_text, n, npat, pats, ms, outs.data(), dev_cap.data(), counts, c->scan_stream)) != BMX_OK) return rc;
+            bool grow = false;
+            for (int32_t k = 0; k < npat; ++k) {
+                const int64_t need = std::min<int64_t>(cap_of(k), (int64_t)counts[k]);
+                if (need > dev_cap[(size_t)k]) {
+                    dev_cap[(size_t)k] = need;
+                    grow = true;
+                }
+            }
+            if (!grow) {
+                for (int32_t k = 0; k < npat; ++k) {
+                    const int64_t ncopy = std::min<int64_t>({(int64_t)counts[k], dev_cap[(size_t)k], cap_of(k)});
+                    if (ncopy > 0) BMX_CUDA(cudaMemcpyAsync(pos_out[k], outs[(size_t)k], (size_t)ncopy * 8, cudaMemcpyDeviceToHost, c->scan_stream));
+                }
+                BMX_CUDA(cudaStreamSynchronize(c->scan_stream));
+                return BMX_OK;
+            }
+        }
+        return fail(BMX_E_CUDA, "bmx_search_multi: position buffers did not converge");
+    }
+    for (int32_t k = 0; k < npat; ++k) {
         if (n < ms[k]) continue;
         uint64_t count = 0;
         int64_t dev_cap = 0;

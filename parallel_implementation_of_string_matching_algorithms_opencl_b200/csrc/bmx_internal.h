@@ -4,6 +4,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <vector_types.h>   // uint2 (CUDA toolkit header, plain C++)
+
 #include "../../include/bmx.h"
 
 namespace bmx {
@@ -78,6 +80,15 @@ struct ScanArgs {
     unsigned long long *carry_out;         // carry_in + hits of this scan (block-scan kernel)
     unsigned long long *count_acc;         // count-only mode: running total over the chained scans (last CTA adds scan_count)
     unsigned long long *scan_count;        // count-only mode: this scan's hits, atomically accumulated; zeroed per launch
+    // multi-pattern variant (kMulti): one shared candidate table for all K patterns, staged into shared memory
+    const uint32_t *g_mbits;               // bitmap over the top kMultiBitmapLog2 bits of the q-gram hash
+    const uint2 *g_mtable;                 // exact table, open addressing: {hash, 0x80000000 | k << 2 | r}; y == 0: empty
+    const uint2 *g_mdir;                   // per pattern: {byte offset into g_mblob, length}
+    const uint8_t *g_mblob;                // the patterns, each 4-byte aligned and followed by 8 bytes of padding
+    unsigned long long *mcounts;           // per-pattern hit counters (exact; zeroed by the host per search)
+    uint32_t npat;
+    uint32_t hmul2;                        // multiplier of the third word (grams of 9..12 bytes, m_min >= 12); 0: two-word grams
+    uint32_t multi_smem;                   // bytes of dynamic shared memory between the control block and the stages
     unsigned long long *host_count;        // host-mapped word: the last CTA of every scan also stores the running count there (finish() reads it without a copy)
     // find-first mode (count-only kernels): key = epoch << 47 | (2^47-1 - position), combined with atomicMax, so a
     // stale word of an earlier search never needs clearing; producers stop fetching tiles behind the best hit
@@ -112,6 +123,16 @@ int launch_partition_count(const int64_t *d_pos, const unsigned long long *d_cou
 void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, ScanArgs *args);
 
 constexpr uint32_t kHashMul = 0x9E3779B1u;
+// multi-pattern candidate table
+constexpr int kMultiMaxPatterns = 64;
+constexpr int kMultiBitmapLog2 = 18;                                   // 2^18 bits = 32 KiB
+constexpr int kMultiBitmapWords = 1 << (kMultiBitmapLog2 - 5);
+constexpr int kMultiSlotsLog2 = 9;                                     // 512 slots for <= 256 (pattern, residue) entries
+constexpr int kMultiSlots = 1 << kMultiSlotsLog2;
+constexpr uint32_t kMultiSlotMul = 0x85EBCA6Bu;
+constexpr uint32_t kHashMul2 = 0xC2B2AE3Du;
+constexpr size_t kMultiSmemBytes = (size_t)kMultiBitmapWords * 4 + (size_t)kMultiSlots * 8 + (size_t)kMultiMaxPatterns * 8;
+constexpr int BMX_VARIANT_MULTI_INTERNAL = 4;                          // not part of the public bmx_variant enum
 constexpr unsigned long long kFindMask = (1ull << 47) - 1;   // find-first keys: positions below 2^47
 
 }  // namespace bmx

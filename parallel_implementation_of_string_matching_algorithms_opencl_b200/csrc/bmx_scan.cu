@@ -192,7 +192,7 @@ __device__ __forceinline__ uint32_t valid_bits(int64_t p0, int64_t vmin, int64_t
 // ---------------------------------------------------------------------------------------------
 // The scan kernel
 // ---------------------------------------------------------------------------------------------
-enum : int { kQgram = 1, kWindow = 2, kShiftAnd = 3 };
+enum : int { kQgram = 1, kWindow = 2, kShiftAnd = 3, kMulti = 4 };
 
 // WINDOW: the 4-byte window that starts s bytes into `lo` (continuing in `hi`).  (Building the
 // shifted windows on the FMA pipe with IMAD.HI/IMAD instead of SHF was measured 13 % slower.)
@@ -301,9 +301,75 @@ __device__ __forceinline__ uint32_t shiftand_chunk(const uint8_t *tp, int32_t m,
     return hits;
 }
 
+// ---- multi-pattern variant: one probe per aligned word, independent of the number of patterns ---------------
+// h = W[j] + hmul * W[j+1] as in QGRAM (one gram length for all patterns); bit (h >> 14) of a 2^18-bit bitmap in
+// shared memory says "some pattern has a q-gram with these top hash bits at some residue".  Only flagged words
+// go on to the exact table {hash -> (pattern, residue)} and from there to a plain comparison with that pattern.
+struct MultiSmem {
+    const uint32_t *bits;
+    const uint2 *table;
+    const uint2 *dir;
+};
+__device__ __forceinline__ uint32_t multi_probe(const uint32_t *bits, uint32_t h)
+{
+    return __funnelshift_r(bits[h >> (32 - kMultiBitmapLog2 + 5)], 0u, h >> (32 - kMultiBitmapLog2));  // bit 0 = the flag
+}
+__device__ __forceinline__ bool multi_any(const uint4 &w, uint32_t w4, uint32_t w5, uint32_t k1, uint32_t k2, const uint32_t *bits)
+{
+    // grams of up to 12 bytes: the third word joins the hash when every pattern is long enough (k2 != 0), which is
+    // what keeps small alphabets selective (4^-12 instead of 4^-8 per gram on DNA)
+    const uint32_t f = multi_probe(bits, w.x + k1 * w.y + k2 * w.z) | multi_probe(bits, w.y + k1 * w.z + k2 * w.w) |
+                       multi_probe(bits, w.z + k1 * w.w + k2 * w4) | multi_probe(bits, w.w + k1 * w4 + k2 * w5);
+    return (f & 1u) != 0u;
+}
+// Exact check of one 16-byte chunk (start positions c-3 .. c+12, c = chunk_v): returns the union hit mask and
+// bumps the per-pattern counters.  Every start position is examined by exactly one thread of the grid.
+__device__ __noinline__ uint32_t multi_chunk(const ScanArgs &A, const MultiSmem &M, const uint4 &w, uint32_t w4, uint32_t w5,
+                                             int64_t chunk_v, const uint8_t *vbase)
+{
+    const uint32_t ww[6] = {w.x, w.y, w.z, w.w, w4, w5};
+    uint32_t hits = 0;
+#pragma unroll 1
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t h = ww[j] + A.hmul * ww[j + 1] + A.hmul2 * ww[j + 2];
+        if (!(multi_probe(M.bits, h) & 1u)) continue;
+        for (uint32_t slot = (h * kMultiSlotMul) >> (32 - kMultiSlotsLog2);; slot = (slot + 1) & (kMultiSlots - 1)) {
+            const uint2 e = M.table[slot];
+            if (e.y == 0u) break;
+            if (e.x != h) continue;
+            const uint32_t k = (e.y >> 2) & 0xFFFFu, r = e.y & 3u;
+            const uint2 d = M.dir[k];
+            const int32_t mk = (int32_t)d.y;
+            const int64_t p = chunk_v + 4 * j - (int64_t)r;
+            if (p < A.vmin || p > A.vmax || p + mk > A.vlen) continue;
+            const uint8_t *pk = A.g_mblob + d.x;
+            bool same = true;
+            int32_t i = 0;
+            for (; same && i + 4 <= mk; i += 4) same = load_u32_unaligned(vbase, p + i) == *reinterpret_cast<const uint32_t *>(pk + i);
+            for (; same && i < mk; ++i) same = vbase[p + i] == pk[i];
+            if (same) {
+                hits |= 1u << (4 * j + 3 - (int)r);
+                atomicAdd(A.mcounts + k, 1ull);
+            }
+        }
+    }
+    return hits;
+}
+
 // Loads one 2 KiB segment the way every filter wants it: 4 x LDS.128 per lane (conflict-free)
 // plus the word that follows each 16-byte chunk (next lane's first word; lane 31 continues in
 // lane 0's next slab or behind the segment, so lane 0 feeds that word into the rotation).
+// The second word after each chunk (three-word grams of the multi-pattern variant), same rotation as w4.
+__device__ __forceinline__ void load_second_after(const uint8_t *sp, int lane, const uint4 (&w)[4], uint32_t (&w5)[4])
+{
+    const uint32_t after2 = *reinterpret_cast<const uint32_t *>(sp + kSegBytes + 4);  // broadcast load
+#pragma unroll
+    for (int sl = 0; sl < 4; ++sl) {
+        const uint32_t wrap = sl < 3 ? w[sl < 3 ? sl + 1 : 3].y : after2;
+        w5[sl] = __shfl_sync(0xFFFFFFFFu, lane == 0 ? wrap : w[sl].y, (lane + 1) & 31);
+    }
+}
+
 __device__ __forceinline__ void load_segment(const uint8_t *sp, int lane, uint4 (&w)[4], uint32_t (&w4)[4])
 {
 #pragma unroll
@@ -376,7 +442,7 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
                                                       VerifyCtx vc, int warp, int lane)
 {
     constexpr int WARP_BYTES = TILE / kConsumerWarps;
-    constexpr int OFFS = VARIANT == kQgram ? -3 : 0;
+    constexpr int OFFS = (VARIANT == kQgram || VARIANT == kMulti) ? -3 : 0;
     unsigned long long found = 0;
     uint32_t cand_lanes = 0, tile_total = 0;
     for (int sg = 0; sg < WARP_BYTES / kSegBytes; ++sg) {
@@ -411,17 +477,22 @@ template <int VARIANT, bool FULL8, int TILE, bool POSITIONS>
 __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant__ ScanArgs A)
 {
     constexpr int WARP_BYTES = TILE / kConsumerWarps;   // contiguous bytes owned by one warp
-    constexpr int OFFS = VARIANT == kQgram ? -3 : 0;    // start position of bit 0 relative to the chunk
+    constexpr int OFFS = (VARIANT == kQgram || VARIANT == kMulti) ? -3 : 0;    // start position of bit 0 relative to the chunk
     constexpr int SEGS = WARP_BYTES / kSegBytes;        // 2 KiB segments per warp per tile
     static_assert(SEGS >= 1 && SEGS * kSegBytes * kConsumerWarps == TILE, "tile must be a multiple of 16 KiB");
 
     extern __shared__ __align__(128) uint8_t smem[];
     SmemCtl *ctl = reinterpret_cast<SmemCtl *>(smem);
-    uint8_t *stages = smem + kCtlBytes;
+    uint8_t *stages = smem + kCtlBytes + (VARIANT == kMulti ? A.multi_smem : 0u);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t S = A.stages;
+    // multi-pattern variant: the shared candidate table sits between the control block and the stages
+    MultiSmem M;
+    M.bits = reinterpret_cast<const uint32_t *>(smem + kCtlBytes);
+    M.table = reinterpret_cast<const uint2 *>(smem + kCtlBytes + (size_t)kMultiBitmapWords * 4);
+    M.dir = reinterpret_cast<const uint2 *>(smem + kCtlBytes + (size_t)kMultiBitmapWords * 4 + (size_t)kMultiSlots * 8);
 
     // Fetches one tile (plus the 16 bytes in front of it and the halo behind it) into pipeline slot s.
     auto fetch_tile = [&](uint32_t tile, uint32_t s) {
@@ -470,6 +541,15 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     }
     if (VARIANT == kShiftAnd) {
         for (int i = tid; i < 256; i += kThreads) ctl->sa_mask[i] = 0u;
+    }
+    if (VARIANT == kMulti) {
+        uint4 *dst = reinterpret_cast<uint4 *>(smem + kCtlBytes);
+        const uint4 *b4 = reinterpret_cast<const uint4 *>(A.g_mbits), *t4 = reinterpret_cast<const uint4 *>(A.g_mtable),
+                    *d4 = reinterpret_cast<const uint4 *>(A.g_mdir);
+        constexpr int NB = kMultiBitmapWords / 4, NT = kMultiSlots / 2, ND = kMultiMaxPatterns / 2;
+        for (int i = tid; i < NB; i += kThreads) dst[i] = b4[i];
+        for (int i = tid; i < NT; i += kThreads) dst[NB + i] = t4[i];
+        for (int i = tid; i < ND; i += kThreads) dst[NB + NT + i] = d4[i];
     }
     __syncthreads();
     if (VARIANT == kShiftAnd) {
@@ -520,12 +600,17 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         // every start position owned by this tile may be reported (false only at the text's ends)
         const bool all_valid = tile_v0 + OFFS >= A.vmin && tile_v0 + (TILE - 1) + OFFS <= A.vmax;
 
-        if (VARIANT != kShiftAnd && dense_mode) {
-            const VerifyCtx vc{vbase, pat, bad, good, exact_filter, all_valid};
-            const unsigned long long r = dense_tile<VARIANT, FULL8, TILE, POSITIONS>(A, st, tile_v0, vc, warp, lane);
-            dense_mode = (r >> 63) != 0;
-            if (!POSITIONS) my_count += r & ~(1ull << 63);
-        } else {
+        bool took_dense = false;
+        if constexpr (VARIANT != kShiftAnd && VARIANT != kMulti) {
+            if (dense_mode) {
+                const VerifyCtx vc{vbase, pat, bad, good, exact_filter, all_valid};
+                const unsigned long long r = dense_tile<VARIANT, FULL8, TILE, POSITIONS>(A, st, tile_v0, vc, warp, lane);
+                dense_mode = (r >> 63) != 0;
+                if (!POSITIONS) my_count += r & ~(1ull << 63);
+                took_dense = true;
+            }
+        }
+        if (!took_dense) {
             uint32_t cand_lanes = 0, tile_total = 0;
 #pragma unroll
             for (int sg = 0; sg < SEGS; ++sg) {
@@ -547,14 +632,22 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                     uint4 w[4];
                     uint32_t w4[4];
                     load_segment(st + seg_off, lane, w, w4);
+                    uint32_t w5[4] = {0u, 0u, 0u, 0u};
+                    if (VARIANT == kMulti && A.hmul2 != 0u) load_second_after(st + seg_off, lane, w, w5);
                     bool any[4];
 #pragma unroll
-                    for (int sl = 0; sl < 4; ++sl) any[sl] = filter_any<VARIANT, FULL8>(w[sl], w4[sl], A);
+                    for (int sl = 0; sl < 4; ++sl)
+                        any[sl] = VARIANT == kMulti ? multi_any(w[sl], w4[sl], w5[sl], A.hmul, A.hmul2, M.bits) : filter_any<VARIANT, FULL8>(w[sl], w4[sl], A);
                     const uint32_t vote = __ballot_sync(0xFFFFFFFFu, any[0] | any[1] | any[2] | any[3]);
                     if (vote) {  // warp-uniform and rare: the common path ends at this branch
 #pragma unroll
                         for (int sl = 0; sl < 4; ++sl) {
-                            if (any[sl]) {
+                            if (VARIANT == kMulti) {
+                                if (any[sl]) {
+                                    hm[sl] = multi_chunk(A, M, w[sl], w4[sl], w5[sl], seg_p0 + sl * 512 - OFFS, vbase);
+                                    seg_hits += __popc(hm[sl]);
+                                }
+                            } else if (any[sl]) {
                                 const int64_t p0 = seg_p0 + sl * 512;
                                 uint32_t cand = filter_mask<VARIANT, FULL8>(w[sl], w4[sl], A);
                                 if (!all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
@@ -1156,6 +1249,7 @@ static const void *pick_kernel_tile(int variant, bool full8, bool positions)
         if (full8) return positions ? kernel_ptr<kWindow, true, TILE, true>() : kernel_ptr<kWindow, true, TILE, false>();
         return positions ? kernel_ptr<kWindow, false, TILE, true>() : kernel_ptr<kWindow, false, TILE, false>();
     }
+    if (variant == BMX_VARIANT_MULTI_INTERNAL) return positions ? kernel_ptr<kMulti, true, TILE, true>() : kernel_ptr<kMulti, true, TILE, false>();
     return positions ? kernel_ptr<kShiftAnd, true, TILE, true>() : kernel_ptr<kShiftAnd, true, TILE, false>();
 }
 
@@ -1208,32 +1302,36 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     int sm_count = 0, smem_optin = 0, smem_sm = 0;
     if (int rc = device_info(device, &sm_count, &smem_optin, &smem_sm, nullptr)) return rc;
 
-    int tile = env_int("BMX_TILE", 32768);   // profiles/tune_knobs.py: 32 KiB tiles, 2 CTAs/SM, 3 stages
-    if (tile != 16384 && tile != 32768) tile = 32768;
+    const bool multi = variant == BMX_VARIANT_MULTI_INTERNAL;
+    // profiles/tune_knobs.py: 32 KiB tiles, 2 CTAs/SM, 3 stages.  The multi-pattern variant keeps 37 KiB of tables in
+    // shared memory: 16 KiB tiles leave room for a 4-stage ring next to them.
+    int tile = multi ? env_int("BMX_MULTI_TILE", 16384) : env_int("BMX_TILE", 32768);
+    if (tile != 16384 && tile != 32768) tile = multi ? 16384 : 32768;
+    a->multi_smem = multi ? (uint32_t)((kMultiSmemBytes + 127) & ~size_t(127)) : 0u;
     const int ctas_per_sm = std::max(1, std::min(2, env_int("BMX_CTAS_PER_SM", 2)));
 
     // Halo: enough for the filter's look-ahead (one more word; Shift-And reads 16+m-1 bytes per
     // chunk) and, when it fits, for verifying a whole pattern from shared memory.
     a->verify_smem = m <= kHaloSmemMax ? 1u : 0u;
     a->halo = a->verify_smem ? (uint32_t)((m + 15 + 15) & ~15) : 32u;
-    a->pat_smem = m <= kPatSmemMax ? 1u : 0u;
+    a->pat_smem = (!multi && m <= kPatSmemMax) ? 1u : 0u;
     a->stage_stride = (uint32_t)((kPre + tile + (int)a->halo + 127) & ~127);
 
     // 1 KiB per resident CTA is reserved by the driver.
     const size_t budget = std::min<size_t>((size_t)smem_optin, (size_t)smem_sm / ctas_per_sm - 1024);
-    int stages = (int)((budget - kCtlBytes) / a->stage_stride);
+    int stages = (int)((budget - kCtlBytes - a->multi_smem) / a->stage_stride);
     stages = std::min(stages, std::min(kMaxStages, env_int("BMX_STAGES", kMaxStages)));
     if (stages < 2) return fail(BMX_E_NOMEM, "pattern of %d bytes leaves room for %d pipeline stages", m, stages);
     a->stages = (uint32_t)stages;
 
     out->variant = variant;
     out->tile_bytes = tile;
-    out->smem_bytes = kCtlBytes + (size_t)stages * a->stage_stride;
+    out->smem_bytes = kCtlBytes + a->multi_smem + (size_t)stages * a->stage_stride;
     const int64_t tiles = (a->vlen + tile - 1) / tile;
     a->num_tiles = (uint32_t)tiles;
     a->num_segs = (uint32_t)(tiles * (tile / kSegBytes));
     a->num_blocks = (a->num_segs + kBlockSegs - 1) / kBlockSegs;
-    a->owner_offset = variant == BMX_VARIANT_QGRAM ? -3 : 0;
+    a->owner_offset = (variant == BMX_VARIANT_QGRAM || multi) ? -3 : 0;
     // BMX_SPARE_SMS leaves SMs free for concurrently running kernels (the NCCL collectives of a
     // multi-GPU pipeline cannot start while a persistent grid holds every SM)
     const int spare = std::max(0, std::min(sm_count - 1, env_int("BMX_SPARE_SMS", 0)));

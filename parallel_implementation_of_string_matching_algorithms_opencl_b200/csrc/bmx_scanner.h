@@ -11,7 +11,8 @@
 struct bmx_scanner {
     int device = 0;
     // per-pattern state
-    int32_t m = 0;
+    int32_t m = 0;             // pattern length (multi-pattern mode: the shortest one -- it bounds the start positions of a scan)
+    int32_t m_halo = 0;        // multi-pattern mode: the longest pattern (sizes the staged halo); 0 = m
     int variant = 0;
     int requested_variant = -1;   // variant argument of the set_pattern call that built the block below (-1: nothing cached)
     int qgram_knob = -1;          // BMX_QGRAM_UNIFORM at that time (a measurement knob that changes the filter constants)

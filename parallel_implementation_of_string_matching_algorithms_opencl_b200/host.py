@@ -177,6 +177,29 @@ def search_multi(text, patterns, max_positions: int | None = None, device: int |
     return [(int(counts[i]), bufs[i][: min(int(counts[i]), caps[i])]) for i in range(k)]
 
 
+def search_multi_device(text, patterns, max_positions: int = 0, stream=None):
+    """K patterns in one pass over a CUDA uint8 tensor (bmx_search_multi_device).  Returns
+    [(count, positions CUDA tensor or None)] in pattern order; max_positions entries of room per pattern (0: counts only)."""
+    import torch
+
+    lib = _lib.load()
+    pats = [_as_bytes(p) for p in patterns]
+    if not text.is_cuda or text.dtype != torch.uint8 or not text.is_contiguous():
+        raise TypeError("search_multi_device() needs a contiguous CUDA uint8 tensor")
+    k, n = len(pats), text.numel()
+    with torch.cuda.device(text.device):
+        outs = [torch.empty(int(max_positions), dtype=torch.int64, device=text.device) if max_positions else None for _ in pats]
+        c_pats = (ctypes.c_char_p * k)(*pats)
+        c_ms = (c_int32 * k)(*[len(p) for p in pats])
+        c_pos = (c_void_p * k)(*[o.data_ptr() if o is not None else None for o in outs])
+        c_caps = (c_int64 * k)(*[int(max_positions)] * k)
+        counts = (c_uint64 * k)()
+        s = stream if stream is not None else torch.cuda.current_stream(text.device)
+        check(lib.bmx_search_multi_device(c_void_p(text.data_ptr() if n else 0), n, k, c_pats, c_ms, c_pos, c_caps, counts,
+                                          c_void_p(s.cuda_stream)))
+    return [(int(counts[i]), None if outs[i] is None else outs[i][: min(int(counts[i]), int(max_positions))]) for i in range(k)]
+
+
 def find_first(text, pattern) -> int:
     """Smallest start position of pattern in HOST text, or -1 -- the early-exit "first occurrence" query of
     the vendored CUDA sample (CUDA/Parallel-Programs-master/cuda/boyer-moore/boyer-moore.cu:62-86), equal to

@@ -538,6 +538,67 @@ def test_search_multi_shares_one_ingest(bmx, oracle, monkeypatch):
         bmx.search_multi(b"abc", [b"a", b""])
 
 
+def test_multi_pattern_single_pass(bmx, oracle, dev):
+    """K patterns in ONE pass (shared candidate table, union emission, per-pattern split) against
+    K serial oracle searches: eligible sets (7 <= m <= 4096, K <= 64) through the device and the host entry point,
+    patterns that are prefixes of each other (two patterns matching at the same start), duplicates, patterns
+    sharing q-grams, capped and count-only outputs, a dense text that makes the union list and the outputs grow."""
+    rnd = random.Random(4242)
+    for it in range(10):
+        sigma = rnd.choice([2, 4, 4, 26, 256])
+        n = rnd.choice([rnd.randint(50, 3000), rnd.randint(100_000, 4_000_000)])
+        text = np.random.default_rng(100 + it).integers(0, sigma, n, dtype=np.uint8) + (65 if sigma < 200 else 0)
+        K = rnd.choice([1, 2, 5, 16, 64])
+        pats = []
+        while len(pats) < K:
+            m = rnd.choice([7, 8, 9, 10, 11, 12, 16, 31, 32, 33, 64, 200])
+            if m > n:
+                continue
+            o = rnd.randint(0, n - m)
+            kind = rnd.random()
+            if kind < 0.6:
+                pats.append(text[o:o + m].tobytes())                            # occurs at least once
+            elif kind < 0.75 and pats:
+                base = rnd.choice(pats)                                          # a prefix of (or equal to) another pattern
+                pats.append(base[: max(7, rnd.randint(7, len(base)))])
+            elif kind < 0.85 and pats:
+                base = bytearray(rnd.choice(pats))                               # shares most q-grams, differs at the end
+                base[-1] ^= 1
+                pats.append(bytes(base))
+            else:
+                pats.append(bytes(int(x) for x in np.random.default_rng(it * 977 + len(pats)).integers(0, sigma, m, dtype=np.uint8) + (65 if sigma < 200 else 0)))
+        for p_ in pats[: 4]:                                                    # plant a few so that sparse alphabets have hits too
+            o = rnd.randint(0, n - len(p_))
+            text[o:o + len(p_)] = np.frombuffer(p_, dtype=np.uint8)
+        wants = [oracle.search_np(text, p_, threads=-1) for p_ in pats]
+        td = to_dev(text, dev, misalign=rnd.randint(0, 17))
+        got = bmx.search_multi_device(td, pats, max_positions=n)
+        for k, ((count, pos), want) in enumerate(zip(got, wants)):
+            assert count == want.size and np.array_equal(pos.cpu().numpy(), want), (it, k, len(pats[k]), "device")
+        capped = bmx.search_multi_device(td, pats, max_positions=2)
+        counted = bmx.search_multi_device(td, pats, max_positions=0)
+        host = bmx.search_multi(text, pats)
+        for k, want in enumerate(wants):
+            assert capped[k][0] == want.size and np.array_equal(capped[k][1].cpu().numpy(), want[:2])
+            assert counted[k][0] == want.size and counted[k][1] is None
+            assert host[k][0] == want.size and np.array_equal(host[k][1], want), (it, k, "host")
+    # dense: every start matches both patterns; the union list and the per-pattern buffers start small and must grow
+    dense = np.full(2_500_000, ord("a"), dtype=np.uint8)
+    dense[2_000_000] = ord("b")
+    pats = [b"a" * 7, b"a" * 12, b"aaaaaab"]
+    wants = [oracle.search_np(dense, p_, threads=-1) for p_ in pats]
+    for k, (count, pos) in enumerate(bmx.search_multi(dense, pats)):
+        assert count == wants[k].size and np.array_equal(pos, wants[k])
+    got = bmx.search_multi_device(to_dev(dense, dev), pats, max_positions=dense.size)
+    for k, (count, pos) in enumerate(got):
+        assert count == wants[k].size and np.array_equal(pos.cpu().numpy(), wants[k])
+    # an ineligible set (a 3-byte pattern) takes the pattern-by-pattern route with the same results
+    mixed = [b"aaa", b"a" * 9]
+    for k, (count, pos) in enumerate(bmx.search_multi_device(to_dev(dense, dev), mixed, max_positions=10)):
+        want = oracle.search_np(dense, mixed[k], threads=-1)
+        assert count == want.size and np.array_equal(pos.cpu().numpy(), want[:10])
+
+
 def test_abi_device_entry_point_raw(bmx, oracle, dev):
     """bmx_search_device exactly as a C caller would use it (ctypes, raw pointers)."""
     lib = bmx._lib.load()
