@@ -66,6 +66,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._armed = False
         self._stop = threading.Event()
         self._thread = None
         try:
@@ -93,6 +94,9 @@ class ClockSampler:
             "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
         }
         while not self._stop.is_set():
+            if not self._armed:          # started before the barrier (NVML set-up costs milliseconds), sampling only the timed region
+                time.sleep(0.0002)
+                continue
             try:
                 self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
                 get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
@@ -109,6 +113,9 @@ class ClockSampler:
             self._thread = threading.Thread(target=self._run, daemon=True)
             self._thread.start()
         return self
+
+    def arm(self):
+        self._armed = True
 
     def __exit__(self, *a):
         self._stop.set()
@@ -301,6 +308,17 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: there is no CPU path"
+    # Placement: with fewer ranks than GPUs the ranks are spread over the box (every (G/N)-th GPU) instead of packed on
+    # GPUs 0..N-1: on the 8-GPU boxes of this pool GPUs 0-3 share one ~115 GB/s path to host memory while 4-7 each get
+    # their full 55 GB/s (profiles/ingest_topology_r02.txt), so four packed ranks ingest at 29 GB/s each and four
+    # spread ranks at 54 GB/s.  The device-resident numbers do not depend on it.  BMX_BENCH_PLACEMENT=packed restores 0..N-1.
+    local_rank = local
+    ngpu = torch.cuda.device_count()
+    placement = "packed"
+    if world > 1 and ngpu > world and ngpu % world == 0 and os.environ.get("BMX_BENCH_PLACEMENT", "spread") == "spread" \
+            and int(os.environ.get("LOCAL_WORLD_SIZE", world)) == world:
+        local = local_rank * (ngpu // world)
+        placement = f"spread (every {ngpu // world}th of {ngpu} GPUs)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     numa = bd.bind_to_device_numa(local) if not args.no_numa_bind else None   # pinned text + staging threads next to the GPU's PCIe root
@@ -391,13 +409,19 @@ def run_ours(args):
     count, stats = scanner.finish(stream=stream)
     ok = verify_hits(torch, text, lo, pat, pos, count, cap)
 
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    # Everything that costs host time (NVML set-up: milliseconds, and it contends across processes) happens BEFORE the
+    # barrier: round 1's "3.4 ms one-off at 8 GPUs" was start skew between the ranks -- each rank initialised NVML
+    # between the barrier and its first event, and the ranks that started early waited in their first exchange
+    # for the one that started last (profiles/r02_n8_timeline.txt).
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     scanner.set_timing(0)          # no event records between the kernels of the headline loop (they cost ~10 us/step)
     state["host"] = [0.0, 0.0, 0.0]
     with ClockSampler(local) as clk:
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        clk.arm()
         t_host0 = time.perf_counter()
         e0.record()
         for _ in range(args.steps):
@@ -541,7 +565,7 @@ def run_ours(args):
                        "alphabet": w["alphabet"], "plants": int(len(plants)), "hits": int(total_hits), "oracle_hits": oracle_hits,
                        "variant": stats["variant"], "tile_bytes": stats["tile_bytes"], "stages": stats["stages"],
                        "grid": stats["grid"], "l2": "inputs larger than L2 (no flush needed)" if w["n"] > (256 << 20) else "input fits L2: flushless, see DESIGN.md",
-                       "verified": bool(ok), "verified_by": verified_by, "exchange": exchange_kind,
+                       "verified": bool(ok), "verified_by": verified_by, "exchange": exchange_kind, "placement": placement, "gpu_index": local,
                        "numa_node": numa, "parallelism": f"shard{world}" if world > 1 else "single"},
             "roofline": {"bound": "hbm", "achieved": rf["achieved"], "peak": peak, "unit": "GB/s", "frac": rf["frac"],
                          "traffic": traffic, "peak_source": peak_src, "kernel_ms": rf["kernel_ms"],

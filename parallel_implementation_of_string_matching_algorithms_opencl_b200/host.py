@@ -121,12 +121,13 @@ def _first_cap(n: int, m: int) -> int:
 
 
 def search_device(text, pattern, pos_out=None, max_positions: int | None = None, pos_base: int = 0,
-                  variant="auto", stream=None):
+                  variant="auto", stream=None, timing: bool = True):
     """Scan a CUDA uint8 tensor -- BoyreMoore.cpp:258-286.  Returns (count, positions, stats).
 
     pos_out: optional preallocated int64 CUDA tensor; otherwise max_positions (default 0 =
     count-only) entries are allocated.  positions is the filled prefix of that tensor (or None).
     Every reported position has pos_base added (multi-GPU shards report global offsets).
+    timing=False skips the library's CUDA-event instrumentation (a few microseconds per call): stats is then {}.
     """
     import torch
 
@@ -146,9 +147,9 @@ def search_device(text, pattern, pos_out=None, max_positions: int | None = None,
         stats = BmxStats()
         check(lib.bmx_search_device_ex(c_void_p(text.data_ptr() if n else 0), n, pat, len(pat), c_int64(pos_base),
                                        c_void_p(pos_out.data_ptr()) if cap else None, cap, ctypes.byref(count),
-                                       _variant(variant), ctypes.byref(stats), c_void_p(s.cuda_stream)))
+                                       _variant(variant), ctypes.byref(stats) if timing else None, c_void_p(s.cuda_stream)))
     found = None if pos_out is None else pos_out[: min(count.value, cap)]
-    return count.value, found, stats.as_dict()
+    return count.value, found, (stats.as_dict() if timing else {})
 
 
 def search_multi(text, patterns, max_positions: int | None = None, device: int | None = None):
