@@ -106,7 +106,7 @@ class ClockSampler:
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.001)
+            time.sleep(0.0005)
 
     def __enter__(self):
         if self.nv:
@@ -678,7 +678,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=50)   # 200 back-to-back 4 GiB scans run into sw_power_cap on these boxes (-1.8 %)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))

@@ -30,7 +30,7 @@ if [[ -f "$cpp_src" && -f "$ref/BoyreMoore/x64/Debug/kernel1.cl" ]]; then
         cat "$here/ref_shim/mid.inc"
         sed -n '153,190p' "$cpp_src"
         cat "$here/ref_shim/tail.inc"
-    } | "$CXX" -O3 -fPIC -shared -std=c++17 -w -x c++ - -o "$here/_ref/libref_bm.so" -lpthread
+    } | "$CXX" -O3 -fPIC -shared -std=c++17 -w -DREF_KERNEL_PATH="\"$ref/BoyreMoore/x64/Debug/kernel1.cl\"" -x c++ - -o "$here/_ref/libref_bm.so" -lpthread
     echo "built $here/_ref/libref_bm.so (reference code compiled from $ref)"
     "$CXX" -O3 -w -std=c++17 -I"$here/ref_shim" "$cpp_src" -o "$here/_ref/BoyreMoore_ref"
     echo "built $here/_ref/BoyreMoore_ref (unmodified BoyreMoore.cpp + stub CL/cl2.hpp)"

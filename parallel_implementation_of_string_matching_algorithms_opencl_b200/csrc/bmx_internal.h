@@ -88,6 +88,7 @@ struct ScanArgs {
     unsigned long long *mcounts;           // per-pattern hit counters (exact; zeroed by the host per search)
     uint32_t npat;
     uint32_t hmul2;                        // multiplier of the third word (grams of 9..12 bytes, m_min >= 12); 0: two-word grams
+    uint32_t multi_blob_smem;              // bytes of g_mblob that fit the control block's good-suffix area (multiple of 16; 0: read from global)
     uint32_t multi_smem;                   // bytes of dynamic shared memory between the control block and the stages
     unsigned long long *host_count;        // host-mapped word: the last CTA of every scan also stores the running count there (finish() reads it without a copy)
     // find-first mode (count-only kernels): key = epoch << 47 | (2^47-1 - position), combined with atomicMax, so a

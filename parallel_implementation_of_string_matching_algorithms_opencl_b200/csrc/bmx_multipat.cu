@@ -183,6 +183,8 @@ int multi_scan_resident(ThreadCtx &c, const unsigned char *d_text, int64_t n, in
     s->proto.g_mblob = d_im + im.off_blob;
     s->proto.mcounts = reinterpret_cast<unsigned long long *>(d_im + im.off_counts);
     s->proto.npat = (uint32_t)npat;
+    const size_t blob_bytes = (im.bytes.size() - im.off_blob + 15) & ~size_t(15);
+    s->proto.multi_blob_smem = blob_bytes <= (size_t)kPatSmemMax * 4 ? (uint32_t)blob_bytes : 0u;   // SmemCtl::good holds kPatSmemMax ints
     s->m = im.m_min;
     s->m_halo = im.m_max;
     s->variant = BMX_VARIANT_MULTI_INTERNAL;

@@ -113,7 +113,7 @@ struct SmemCtl {
     uint32_t scan_dense[kConsumerWarps];
     int32_t bad[256];              // bad-symbol table   (BoyreMoore.cpp:153-162)
     uint32_t sa_mask[256];         // Shift-And occurrence masks
-    int32_t good[kPatSmemMax];     // good-suffix table  (BoyreMoore.cpp:165-190)
+    alignas(16) int32_t good[kPatSmemMax];  // good-suffix table  (BoyreMoore.cpp:165-190); the multi-pattern variant keeps its patterns here
     uint8_t pat[kPatSmemMax];
 };
 constexpr size_t kCtlBytes = (sizeof(SmemCtl) + 127) & ~size_t(127);
@@ -322,43 +322,51 @@ __device__ __forceinline__ bool multi_any(const uint4 &w, uint32_t w4, uint32_t 
                        multi_probe(bits, w.z + k1 * w.w + k2 * w4) | multi_probe(bits, w.w + k1 * w4 + k2 * w5);
     return (f & 1u) != 0u;
 }
-// Exact check of one 16-byte chunk (start positions c-3 .. c+12, c = chunk_v): returns the union hit mask and
-// bumps the per-pattern counters.  Every start position is examined by exactly one thread of the grid.
-__device__ __noinline__ uint32_t multi_chunk(const ScanArgs &A, const MultiSmem &M, const uint4 &w, uint32_t w4, uint32_t w5,
-                                             int64_t chunk_v, const uint8_t *vbase)
+// A word whose hash is flagged AND whose home slot of the exact table is occupied: walk the probe sequence and compare
+// the text with every pattern that has this gram at some residue.  Rare (about K / 128 of the flagged words), out of
+// line, all arguments in registers.  Returns the hit bits of the chunk (bit = start - (chunk_v - 3)).
+__device__ __noinline__ uint32_t multi_word(const ScanArgs &A, const uint2 *table, const uint2 *dir, const uint8_t *blob,
+                                            uint32_t h, int j, int64_t chunk_v, const uint8_t *vbase)
 {
-    const uint32_t ww[6] = {w.x, w.y, w.z, w.w, w4, w5};
     uint32_t hits = 0;
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j) {
-        const uint32_t h = ww[j] + A.hmul * ww[j + 1] + A.hmul2 * ww[j + 2];
-        if (!(multi_probe(M.bits, h) & 1u)) continue;
-        for (uint32_t slot = (h * kMultiSlotMul) >> (32 - kMultiSlotsLog2);; slot = (slot + 1) & (kMultiSlots - 1)) {
-            const uint2 e = M.table[slot];
-            if (e.y == 0u) break;
-            if (e.x != h) continue;
-            const uint32_t k = (e.y >> 2) & 0xFFFFu, r = e.y & 3u;
-            const uint2 d = M.dir[k];
-            const int32_t mk = (int32_t)d.y;
-            const int64_t p = chunk_v + 4 * j - (int64_t)r;
-            if (p < A.vmin || p > A.vmax || p + mk > A.vlen) continue;
-            const uint8_t *pk = A.g_mblob + d.x;
-            bool same = true;
-            int32_t i = 0;
-            for (; same && i + 4 <= mk; i += 4) same = load_u32_unaligned(vbase, p + i) == *reinterpret_cast<const uint32_t *>(pk + i);
-            for (; same && i < mk; ++i) same = vbase[p + i] == pk[i];
-            if (same) {
-                hits |= 1u << (4 * j + 3 - (int)r);
-                atomicAdd(A.mcounts + k, 1ull);
-            }
+    for (uint32_t slot = (h * kMultiSlotMul) >> (32 - kMultiSlotsLog2);; slot = (slot + 1) & (kMultiSlots - 1)) {
+        const uint2 e = table[slot];
+        if (e.y == 0u) break;
+        if (e.x != h) continue;
+        const uint32_t k = (e.y >> 2) & 0xFFFFu, r = e.y & 3u;
+        const uint2 d = dir[k];
+        const int32_t mk = (int32_t)d.y;
+        const int64_t p = chunk_v + 4 * j - (int64_t)r;
+        if (p < A.vmin || p > A.vmax || p + mk > A.vlen) continue;
+        const uint8_t *pk = blob + d.x;
+        bool same = true;
+        int32_t i = 0;
+        for (; same && i + 4 <= mk; i += 4) same = load_u32_unaligned(vbase, p + i) == *reinterpret_cast<const uint32_t *>(pk + i);
+        for (; same && i < mk; ++i) same = vbase[p + i] == pk[i];
+        if (same) {
+            hits |= 1u << (4 * j + 3 - (int)r);
+            atomicAdd(A.mcounts + k, 1ull);
         }
     }
     return hits;
 }
+// Exact check of one 16-byte chunk (start positions c-3 .. c+12, c = chunk_v): returns the union hit mask and bumps the
+// per-pattern counters.  Every start position is examined by exactly one thread of the grid.  A false positive of the
+// bitmap dies here at ONE shared-memory load (its home slot in the exact table is empty), without a call.
+__device__ __forceinline__ uint32_t multi_chunk(const ScanArgs &A, const MultiSmem &M, const uint8_t *blob, const uint4 &w, uint32_t w4,
+                                                uint32_t w5, int64_t chunk_v, const uint8_t *vbase)
+{
+    const uint32_t k1 = A.hmul, k2 = A.hmul2;
+    const uint32_t h[4] = {w.x + k1 * w.y + k2 * w.z, w.y + k1 * w.z + k2 * w.w, w.z + k1 * w.w + k2 * w4, w.w + k1 * w4 + k2 * w5};
+    uint32_t hits = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if ((multi_probe(M.bits, h[j]) & 1u) && M.table[(h[j] * kMultiSlotMul) >> (32 - kMultiSlotsLog2)].y != 0u)
+            hits |= multi_word(A, M.table, M.dir, blob, h[j], j, chunk_v, vbase);
+    }
+    return hits;
+}
 
-// Loads one 2 KiB segment the way every filter wants it: 4 x LDS.128 per lane (conflict-free)
-// plus the word that follows each 16-byte chunk (next lane's first word; lane 31 continues in
-// lane 0's next slab or behind the segment, so lane 0 feeds that word into the rotation).
 // The second word after each chunk (three-word grams of the multi-pattern variant), same rotation as w4.
 __device__ __forceinline__ void load_second_after(const uint8_t *sp, int lane, const uint4 (&w)[4], uint32_t (&w5)[4])
 {
@@ -493,6 +501,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     M.bits = reinterpret_cast<const uint32_t *>(smem + kCtlBytes);
     M.table = reinterpret_cast<const uint2 *>(smem + kCtlBytes + (size_t)kMultiBitmapWords * 4);
     M.dir = reinterpret_cast<const uint2 *>(smem + kCtlBytes + (size_t)kMultiBitmapWords * 4 + (size_t)kMultiSlots * 8);
+    const uint8_t *mblob = (VARIANT == kMulti && A.multi_blob_smem) ? reinterpret_cast<const uint8_t *>(ctl->good) : A.g_mblob;
 
     // Fetches one tile (plus the 16 bytes in front of it and the halo behind it) into pipeline slot s.
     auto fetch_tile = [&](uint32_t tile, uint32_t s) {
@@ -550,6 +559,11 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         for (int i = tid; i < NB; i += kThreads) dst[i] = b4[i];
         for (int i = tid; i < NT; i += kThreads) dst[NB + i] = t4[i];
         for (int i = tid; i < ND; i += kThreads) dst[NB + NT + i] = d4[i];
+        if (A.multi_blob_smem) {   // the patterns themselves ride in the good-suffix area of the control block (unused here)
+            uint4 *bd = reinterpret_cast<uint4 *>(ctl->good);
+            const uint4 *bs = reinterpret_cast<const uint4 *>(A.g_mblob);
+            for (uint32_t i = tid; i < A.multi_blob_smem / 16u; i += kThreads) bd[i] = bs[i];
+        }
     }
     __syncthreads();
     if (VARIANT == kShiftAnd) {
@@ -644,7 +658,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                         for (int sl = 0; sl < 4; ++sl) {
                             if (VARIANT == kMulti) {
                                 if (any[sl]) {
-                                    hm[sl] = multi_chunk(A, M, w[sl], w4[sl], w5[sl], seg_p0 + sl * 512 - OFFS, vbase);
+                                    hm[sl] = multi_chunk(A, M, mblob, w[sl], w4[sl], w5[sl], seg_p0 + sl * 512 - OFFS, vbase);
                                     seg_hits += __popc(hm[sl]);
                                 }
                             } else if (any[sl]) {

@@ -4,7 +4,7 @@
 // helpers :16-60 (good-suffix table).  The reference derives the good-suffix shifts with nested
 // rescans (O(m^3) worst case, m <= 99); here they come from the classical suffix-length array in
 // O(m), which yields the same strong good-suffix values for every k = 1..m-1
-// (tests/test_tables.py checks this against the reference's own code and against the oracle).
+// (tests/test_host_logic.py checks this against the reference's own code and against the oracle).
 #include "bmx_internal.h"
 
 #include <vector>

@@ -23,7 +23,7 @@ pat = bmx.synth.fill_host(12345, 32, 43, bmx.synth.ALPHABETS["dna"]).tobytes()
 pageable = t.cpu().numpy()
 pinned = torch.from_numpy(pageable).pin_memory()
 for name, buf in (("pinned", pinned), ("pageable", pageable)):
-    for threads in ((None,) if name == "pinned" else (1, 2, 4, 8)):
+    for threads in ((None,) if name == "pinned" else (1, 2, 4, 8, 12, 16, 24, 32)):
         if threads:
             os.environ["BMX_STAGING_THREADS"] = str(threads)
         bmx.search(buf, pat, max_positions=1 << 16)
