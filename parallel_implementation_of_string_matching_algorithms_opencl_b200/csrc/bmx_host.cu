@@ -162,7 +162,7 @@ int ingest_and_scan(ThreadCtx &ctx, int device, const char *text, int64_t n, con
     io->resident = resident;
 
     const bool pinned = is_pinned_host(text);
-    int staging_threads = (int)env_long("BMX_STAGING_THREADS", 8);  // host threads filling a bounce buffer (profiles/e2e_host_memory.py)
+    int staging_threads = (int)env_long("BMX_STAGING_THREADS", 16);  // host threads filling a bounce buffer: 8 -> 39.9, 16 -> 42.8, 32 -> 43.2 GB/s (profiles/e2e_host_memory_r02.txt)
     staging_threads = (int)std::max(1u, std::min<unsigned>((unsigned)std::max(1, std::min(64, staging_threads)), std::thread::hardware_concurrency()));
     if (!pinned && c->bounce_bytes < (size_t)std::min(chunk, n)) {
         for (int b = 0; b < kBounce; ++b) {
