@@ -59,6 +59,7 @@ struct ScanArgs {
     uint32_t hmul;          // QGRAM: hash multiplier K << (32 - 8*(q-4)); the shift drops the bytes beyond the q-gram
     uint32_t hmulr[4];      // QGRAM, 7 <= m <= 10: one multiplier per residue (residue r sees min(8, m - r) bytes)
     uint32_t mulc;          // WINDOW: 2^(32-8q), drops the bytes beyond q
+    uint32_t bcast[3];      // WINDOW, m <= 3: pattern byte k replicated into the four bytes of a word
     // per-pattern block in global memory
     const uint8_t *g_pat;
     const int32_t *g_bad;

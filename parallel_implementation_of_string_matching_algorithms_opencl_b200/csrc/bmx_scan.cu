@@ -201,8 +201,23 @@ __device__ __forceinline__ uint32_t window_at(uint32_t lo, uint32_t hi, int s)
     return s == 0 ? lo : __funnelshift_r(lo, hi, 8 * s);
 }
 
-// FLAG: WINDOW -> q == 4 (m >= 4), no multiply needed; QGRAM -> one hash multiplier for all four residues.
-template <int VARIANT, bool FLAG>
+// WINDOW, m <= 3: four start positions per word at once.  z = OR over k of ((text shifted by k bytes) ^ P[k] in every
+// byte) has a zero byte exactly where all m bytes match; (z & 0x7F..) + 0x7F.. never carries across bytes, so the zero
+// test is exact.  Returns 0x80 in the byte of every matching start position: 3 + 2(m-1) + 3 instructions for four
+// positions instead of a funnel shift, a multiply, a compare and a select each.
+template <int M>   // M = pattern length 1..3: a compile-time constant, so the construction below is branch-free
+__device__ __forceinline__ uint32_t window_flags(uint32_t lo, uint32_t hi, uint32_t b0, uint32_t b1, uint32_t b2)
+{
+    uint32_t z = lo ^ b0;
+    if (M >= 2) z |= __funnelshift_r(lo, hi, 8) ^ b1;
+    if (M >= 3) z |= __funnelshift_r(lo, hi, 16) ^ b2;
+    const uint32_t a = (z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(a | z) & 0x80808080u;
+}
+
+// FLAG: QGRAM -> 1: one hash multiplier for all four residues, 0: one per residue (7 <= m <= 10).
+//       WINDOW -> 1: whole 4-byte windows (m >= 4); 2, 3, 4: m = 1, 2, 3 (byte-parallel flags, window_flags<m>).
+template <int VARIANT, int FLAG>
 __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const ScanArgs &A)
 {
     if (VARIANT == kQgram) {
@@ -233,22 +248,25 @@ __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const Sc
         any |= (h3 == f0) | (h3 == f1) | (h3 == f2) | (h3 == f3);
         return any;
     } else {
-        const uint32_t mc = A.mulc, tg = A.f[0];
+        if (FLAG >= 2) {   // m = FLAG - 1 <= 3
+            constexpr int M = FLAG >= 2 ? FLAG - 1 : 1;
+            const uint32_t b0 = A.bcast[0], b1 = A.bcast[1], b2 = A.bcast[2];
+            return (window_flags<M>(w.x, w.y, b0, b1, b2) | window_flags<M>(w.y, w.z, b0, b1, b2) | window_flags<M>(w.z, w.w, b0, b1, b2) |
+                    window_flags<M>(w.w, w4, b0, b1, b2)) != 0u;
+        }
+        const uint32_t tg = A.f[0];
         const uint32_t ww[5] = {w.x, w.y, w.z, w.w, w4};
         bool any = false;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int sh = 0; sh < 4; ++sh) {
-                const uint32_t x = window_at(ww[j], ww[j + 1], sh);
-                any |= FLAG ? (x == tg) : (x * mc == tg);
-            }
+            for (int sh = 0; sh < 4; ++sh) any |= window_at(ww[j], ww[j + 1], sh) == tg;
         }
         return any;
     }
 }
 
-template <int VARIANT, bool FLAG>
+template <int VARIANT, int FLAG>
 __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, const ScanArgs &A)
 {
     uint32_t mask = 0;
@@ -264,14 +282,19 @@ __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, con
                 mask |= (uint32_t)(hr == A.f[r]) << (4 * j + 3 - r);
             }
         }
+    } else if (FLAG >= 2) {
+        // m = FLAG - 1 <= 3: flags of two words share one multiply that gathers their eight 0x80 bits into one byte
+        // ((c0 >> 4 | c1) * 0x204081 >> 24: bits 3,11,19,27 and 7,15,23,31 land on 24..31 in position order, no carries)
+        constexpr int M = FLAG >= 2 ? FLAG - 1 : 1;
+        const uint32_t b0 = A.bcast[0], b1 = A.bcast[1], b2 = A.bcast[2];
+        const uint32_t c0 = window_flags<M>(ww[0], ww[1], b0, b1, b2), c1 = window_flags<M>(ww[1], ww[2], b0, b1, b2);
+        const uint32_t c2 = window_flags<M>(ww[2], ww[3], b0, b1, b2), c3 = window_flags<M>(ww[3], ww[4], b0, b1, b2);
+        mask = ((((c0 >> 4) | c1) * 0x00204081u) >> 24) | (((((c2 >> 4) | c3) * 0x00204081u) >> 24) << 8);
     } else {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll
-            for (int sh = 0; sh < 4; ++sh) {
-                const uint32_t x = window_at(ww[j], ww[j + 1], sh);
-                mask |= (uint32_t)(FLAG ? (x == A.f[0]) : (x * A.mulc == A.f[0])) << (4 * j + sh);
-            }
+            for (int sh = 0; sh < 4; ++sh) mask |= (uint32_t)(window_at(ww[j], ww[j + 1], sh) == A.f[0]) << (4 * j + sh);
         }
     }
     return mask;
@@ -445,7 +468,7 @@ struct VerifyCtx {
 // a tile without the any-pass and the vote -- every lane builds its masks right away.  Kept out of
 // line so the common path of scan_kernel stays exactly the sparse filter loop.  Returns the hits
 // found (count-only mode adds them up) with bit 63 set while the text is still dense.
-template <int VARIANT, bool FLAG, int TILE, bool POSITIONS>
+template <int VARIANT, int FLAG, int TILE, bool POSITIONS>
 __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const uint8_t *st, int64_t tile_v0,
                                                       VerifyCtx vc, int warp, int lane)
 {
@@ -481,7 +504,7 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
     return found | (cand_lanes >= kDenseLanes * (WARP_BYTES / kSegBytes) ? (1ull << 63) : 0ull);
 }
 
-template <int VARIANT, bool FULL8, int TILE, bool POSITIONS>
+template <int VARIANT, int FULL8, int TILE, bool POSITIONS>
 __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant__ ScanArgs A)
 {
     constexpr int WARP_BYTES = TILE / kConsumerWarps;   // contiguous bytes owned by one warp
@@ -1231,6 +1254,7 @@ void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, Sca
             }
         }
     } else if (variant == BMX_VARIANT_WINDOW) {
+        for (int k = 0; k < 3; ++k) a->bcast[k] = (uint32_t)pat[std::min(k, m - 1)] * 0x01010101u;
         const int q = std::min(m, 4);
         a->mulc = q >= 4 ? 1u : (1u << (32 - 8 * q));
         a->f[0] = le_word(pat, q) * a->mulc;
@@ -1238,36 +1262,42 @@ void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, Sca
 }
 
 // FULL8: WINDOW compares whole 4-byte windows (m >= 4); QGRAM hashes all residues with one multiplier.
-static bool uses_full8(int variant, const ScanArgs &a)
+// The kernels' FLAG parameter: QGRAM 1 = one multiplier for all residues; WINDOW 1 = whole 4-byte windows (m >= 4),
+// 2 / 3 / 4 = m of 1 / 2 / 3 bytes; everything else 1.
+static int uses_full8(int variant, const ScanArgs &a)
 {
-    if (variant == BMX_VARIANT_WINDOW) return a.mulc == 1u;
+    if (variant == BMX_VARIANT_WINDOW) return a.m >= 4 ? 1 : a.m + 1;
     if (variant == BMX_VARIANT_QGRAM)
-        return a.hmulr[0] == a.hmulr[3] && a.hmulr[1] == a.hmulr[3] && a.hmulr[2] == a.hmulr[3];
-    return true;
+        return (a.hmulr[0] == a.hmulr[3] && a.hmulr[1] == a.hmulr[3] && a.hmulr[2] == a.hmulr[3]) ? 1 : 0;
+    return 1;
 }
 
-template <int VARIANT, bool FULL8, int TILE, bool POSITIONS>
+template <int VARIANT, int FULL8, int TILE, bool POSITIONS>
 static const void *kernel_ptr()
 {
     return reinterpret_cast<const void *>(&scan_kernel<VARIANT, FULL8, TILE, POSITIONS>);
 }
 
 template <int TILE>
-static const void *pick_kernel_tile(int variant, bool full8, bool positions)
+static const void *pick_kernel_tile(int variant, int full8, bool positions)
 {
     if (variant == BMX_VARIANT_QGRAM) {
-        if (full8) return positions ? kernel_ptr<kQgram, true, TILE, true>() : kernel_ptr<kQgram, true, TILE, false>();
-        return positions ? kernel_ptr<kQgram, false, TILE, true>() : kernel_ptr<kQgram, false, TILE, false>();
+        if (full8) return positions ? kernel_ptr<kQgram, 1, TILE, true>() : kernel_ptr<kQgram, 1, TILE, false>();
+        return positions ? kernel_ptr<kQgram, 0, TILE, true>() : kernel_ptr<kQgram, 0, TILE, false>();
     }
     if (variant == BMX_VARIANT_WINDOW) {
-        if (full8) return positions ? kernel_ptr<kWindow, true, TILE, true>() : kernel_ptr<kWindow, true, TILE, false>();
-        return positions ? kernel_ptr<kWindow, false, TILE, true>() : kernel_ptr<kWindow, false, TILE, false>();
+        switch (full8) {
+        case 2: return positions ? kernel_ptr<kWindow, 2, TILE, true>() : kernel_ptr<kWindow, 2, TILE, false>();
+        case 3: return positions ? kernel_ptr<kWindow, 3, TILE, true>() : kernel_ptr<kWindow, 3, TILE, false>();
+        case 4: return positions ? kernel_ptr<kWindow, 4, TILE, true>() : kernel_ptr<kWindow, 4, TILE, false>();
+        default: return positions ? kernel_ptr<kWindow, 1, TILE, true>() : kernel_ptr<kWindow, 1, TILE, false>();
+        }
     }
-    if (variant == BMX_VARIANT_MULTI_INTERNAL) return positions ? kernel_ptr<kMulti, true, TILE, true>() : kernel_ptr<kMulti, true, TILE, false>();
-    return positions ? kernel_ptr<kShiftAnd, true, TILE, true>() : kernel_ptr<kShiftAnd, true, TILE, false>();
+    if (variant == BMX_VARIANT_MULTI_INTERNAL) return positions ? kernel_ptr<kMulti, 1, TILE, true>() : kernel_ptr<kMulti, 1, TILE, false>();
+    return positions ? kernel_ptr<kShiftAnd, 1, TILE, true>() : kernel_ptr<kShiftAnd, 1, TILE, false>();
 }
 
-static const void *pick_kernel(int variant, bool full8, int tile, bool positions)
+static const void *pick_kernel(int variant, int full8, int tile, bool positions)
 {
     switch (tile) {
     case 16384: return pick_kernel_tile<16384>(variant, full8, positions);
@@ -1351,7 +1381,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     const int spare = std::max(0, std::min(sm_count - 1, env_int("BMX_SPARE_SMS", 0)));
     out->grid = (int)std::min<int64_t>(tiles, (int64_t)(sm_count - spare) * ctas_per_sm);
 
-    const bool full8 = uses_full8(variant, *a);
+    const int full8 = uses_full8(variant, *a);
     const void *k = pick_kernel(variant, full8, tile, positions);
     if (!k) return fail(BMX_E_BADARG, "no kernel for variant %d tile %d", variant, tile);
     {
@@ -1371,7 +1401,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
 
 int launch_scan(const ScanArgs &a, const ScanLaunch &l, bool positions, void *stream)
 {
-    const bool full8 = uses_full8(l.variant, a);
+    const int full8 = uses_full8(l.variant, a);
     const void *k = pick_kernel(l.variant, full8, l.tile_bytes, positions);
     void *params[] = {const_cast<ScanArgs *>(&a)};
     const cudaError_t e = cudaLaunchKernel(k, dim3((unsigned)l.grid), dim3(kThreads), params, l.smem_bytes,
