@@ -70,6 +70,7 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
+// (A suspend-time hint on try_wait was measured neutral on sparse and mid-density texts alike and is not used.)
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(
@@ -115,6 +116,7 @@ struct SmemCtl {
     uint32_t sa_mask[256];         // Shift-And occurrence masks
     alignas(16) int32_t good[kPatSmemMax];  // good-suffix table  (BoyreMoore.cpp:165-190); the multi-pattern variant keeps its patterns here
     uint8_t pat[kPatSmemMax];
+    uint32_t rpat[kPatSmemMax / 4];  // pattern words from the right end: rpat[i] = P[m-4-4i .. m-4i), little endian
 };
 constexpr size_t kCtlBytes = (sizeof(SmemCtl) + 127) & ~size_t(127);
 
@@ -135,9 +137,13 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t *base, int6
 
 // `wordwise` is set when the text is verified from the staged tile (whose halo makes the aligned word
 // pairs safe to read); long patterns verified from global memory compare byte by byte.
+// `rpat` (shared memory, patterns up to kPatSmemMax bytes): the pattern's words counted from its right end.  With it
+// a step of the right-to-left comparison is ONE new aligned text word (the previous one is kept for the funnel shift),
+// one pattern word and an XOR -- a 25-byte match costs ~60 instructions instead of ~220 with two unaligned word
+// fetches (four loads, two shifts, 64-bit address arithmetic) per step.
 __device__ __noinline__ uint32_t verify_candidates(uint32_t cand, const uint8_t *vbase, int64_t p0, int32_t m,
-                                                   const uint8_t *pat, const int32_t *bad, const int32_t *good,
-                                                   bool wordwise)
+                                                   const uint8_t *pat, const uint32_t *rpat, const int32_t *bad,
+                                                   const int32_t *good, bool wordwise)
 {
     uint32_t hits = 0;
     while (cand) {
@@ -149,14 +155,33 @@ __device__ __noinline__ uint32_t verify_candidates(uint32_t cand, const uint8_t 
         // so the leading zero bytes of the XOR are exactly the matched suffix bytes of that word.
         int32_t k = 0;
         bool differs = false;
-        while (wordwise && k + 4 <= m) {
-            const uint32_t x = load_u32_unaligned(vbase, p + m - 4 - k) ^ load_u32_unaligned(pat, m - 4 - k);
-            if (x) {
-                k += __clz(x) >> 3;
-                differs = true;
-                break;
+        if (wordwise && rpat != nullptr) {
+            const uintptr_t end = reinterpret_cast<uintptr_t>(t) + (uintptr_t)m;      // one past the last text byte
+            const uint32_t *aw = reinterpret_cast<const uint32_t *>(end & ~uintptr_t(3));
+            const int sh = 8 * (int)(end & 3u);
+            uint32_t hi = aw[0];          // the word holding the byte behind the window: inside the staged halo
+            const int32_t steps = m >> 2;
+            for (int32_t i = 0; i < steps; ++i) {
+                const uint32_t lo = *--aw;
+                const uint32_t x = __funnelshift_r(lo, hi, sh) ^ rpat[i];   // text bytes [m-4-4i, m-4i) of the window
+                hi = lo;
+                if (x) {
+                    k += __clz(x) >> 3;
+                    differs = true;
+                    break;
+                }
+                k += 4;
             }
-            k += 4;
+        } else {
+            while (wordwise && k + 4 <= m) {
+                const uint32_t x = load_u32_unaligned(vbase, p + m - 4 - k) ^ load_u32_unaligned(pat, m - 4 - k);
+                if (x) {
+                    k += __clz(x) >> 3;
+                    differs = true;
+                    break;
+                }
+                k += 4;
+            }
         }
         if (!differs)
             while (k < m && t[m - 1 - k] == pat[m - 1 - k]) ++k;
@@ -460,6 +485,7 @@ constexpr uint32_t kDenseLanes = 6;
 
 struct VerifyCtx {
     const uint8_t *vbase, *pat;
+    const uint32_t *rpat;
     const int32_t *bad, *good;
     bool exact_filter, all_valid;
 };
@@ -490,7 +516,7 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
             if (!vc.all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
             any_cand |= cand;
             hm[sl] = 0;
-            if (cand) hm[sl] = vc.exact_filter ? cand : verify_candidates(cand, vc.vbase, p0, A.m, vc.pat, vc.bad, vc.good, A.verify_smem != 0);
+            if (cand) hm[sl] = vc.exact_filter ? cand : verify_candidates(cand, vc.vbase, p0, A.m, vc.pat, vc.rpat, vc.bad, vc.good, A.verify_smem != 0);
             seg_hits += __popc(hm[sl]);
         }
         cand_lanes += __popc(__ballot_sync(0xFFFFFFFFu, any_cand != 0));
@@ -570,6 +596,10 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
             ctl->good[i] = A.g_good[i];
             ctl->pat[i] = A.g_pat[i];
         }
+        for (int i = tid; i < (A.m >> 2); i += kThreads) {   // pattern words counted from the right end
+            const uint8_t *q = A.g_pat + (A.m - 4 - 4 * i);
+            ctl->rpat[i] = (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16) | ((uint32_t)q[3] << 24);
+        }
     }
     if (VARIANT == kShiftAnd) {
         for (int i = tid; i < 256; i += kThreads) ctl->sa_mask[i] = 0u;
@@ -621,6 +651,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     const uint8_t *pat = A.pat_smem ? ctl->pat : A.g_pat;
     const int32_t *bad = A.pat_smem ? ctl->bad : A.g_bad;
     const int32_t *good = A.pat_smem ? ctl->good : A.g_good;
+    const uint32_t *rpat = A.pat_smem ? ctl->rpat : nullptr;
     const bool exact_filter = (VARIANT == kShiftAnd) || (VARIANT == kWindow && A.m <= 4);
     unsigned long long my_count = 0;  // count-only mode
     bool dense_mode = false;          // per warp: candidates in most lanes -> next tile takes dense_tile()
@@ -640,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         bool took_dense = false;
         if constexpr (VARIANT != kShiftAnd && VARIANT != kMulti) {
             if (dense_mode) {
-                const VerifyCtx vc{vbase, pat, bad, good, exact_filter, all_valid};
+                const VerifyCtx vc{vbase, pat, rpat, bad, good, exact_filter, all_valid};
                 const unsigned long long r = dense_tile<VARIANT, FULL8, TILE, POSITIONS>(A, st, tile_v0, vc, warp, lane);
                 dense_mode = (r >> 63) != 0;
                 if (!POSITIONS) my_count += r & ~(1ull << 63);
@@ -689,7 +720,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                                 uint32_t cand = filter_mask<VARIANT, FULL8>(w[sl], w4[sl], A);
                                 if (!all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
                                 if (cand)
-                                    hm[sl] = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, bad, good, A.verify_smem != 0);
+                                    hm[sl] = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, rpat, bad, good, A.verify_smem != 0);
                                 seg_hits += __popc(hm[sl]);
                             }
                         }
