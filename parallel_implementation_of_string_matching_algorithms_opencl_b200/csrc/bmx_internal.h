@@ -53,6 +53,7 @@ struct ScanArgs {
     uint32_t stage_stride;  // bytes between stages in shared memory
     uint32_t halo;          // bytes staged behind a tile
     uint32_t verify_smem;   // 1: candidates are verified from the staged tile, 0: from global
+    uint32_t dense_lanes;   // a warp whose segments held candidates in this many lanes on average builds all masks right away
     uint32_t pat_smem;      // 1: pattern + tables copied to shared memory
     // filter constants
     uint32_t f[4];          // QGRAM: hash of P[r..r+q) for r = 0..3; WINDOW: f[0] = target

@@ -141,14 +141,17 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t *base, int6
 // a step of the right-to-left comparison is ONE new aligned text word (the previous one is kept for the funnel shift),
 // one pattern word and an XOR -- a 25-byte match costs ~60 instructions instead of ~220 with two unaligned word
 // fetches (four loads, two shifts, 64-bit address arithmetic) per step.
-__device__ __noinline__ uint32_t verify_candidates(uint32_t cand, const uint8_t *vbase, int64_t p0, int32_t m,
-                                                   const uint8_t *pat, const uint32_t *rpat, const int32_t *bad,
-                                                   const int32_t *good, bool wordwise)
+// cand holds the candidates of ALL FOUR slabs of the lane's share of a segment (16 bits each, slab sl at bits 16 sl ..):
+// one call per segment instead of one per slab -- candidates of different slabs usually sit in different lanes, and
+// lanes of one call verify concurrently, so a segment with candidates in three slabs pays for one verification, not three.
+__device__ __noinline__ unsigned long long verify_candidates(unsigned long long cand, const uint8_t *vbase, int64_t p0, int32_t m,
+                                                             const uint8_t *pat, const uint32_t *rpat, const int32_t *bad,
+                                                             const int32_t *good, bool wordwise)
 {
-    uint32_t hits = 0;
+    unsigned long long hits = 0;
     while (cand) {
-        const int b = __ffs(cand) - 1;
-        const int64_t p = p0 + b;
+        const int b = __ffsll((long long)cand) - 1;
+        const int64_t p = p0 + (b >> 4) * 512 + (b & 15);   // slab b / 16 starts 512 bytes behind the previous one
         const uint8_t *t = vbase + p;
         // k = number of pattern bytes that match from the right end (kernel1.cl:21-22), found four
         // bytes at a time: in a little-endian word the rightmost text byte is the most significant one,
@@ -187,7 +190,7 @@ __device__ __noinline__ uint32_t verify_candidates(uint32_t cand, const uint8_t 
             while (k < m && t[m - 1 - k] == pat[m - 1 - k]) ++k;
         int32_t shift;
         if (k == m) {
-            hits |= 1u << b;
+            hits |= 1ull << b;
             shift = 1;
         } else {
             int32_t d1 = bad[t[m - 1]] - k;
@@ -198,8 +201,10 @@ __device__ __noinline__ uint32_t verify_candidates(uint32_t cand, const uint8_t 
                 shift = d2 > d1 ? d2 : d1;
             }
         }
-        const int nb = b + shift;
-        cand = nb >= 32 ? 0u : ((cand >> nb) << nb);
+        // the shift skips candidates of THIS slab only (the next slab's start positions lie 512 bytes further on)
+        const int in_slab = (b & 15) + shift;
+        const int nb = in_slab >= 16 ? (b | 15) + 1 : b + shift;
+        cand = nb >= 64 ? 0ull : ((cand >> nb) << nb);
     }
     return hits;
 }
@@ -481,7 +486,10 @@ __device__ __forceinline__ long long first_so_far(const ScanArgs &A)
 // A warp switches to dense_tile() for its next tile when, on average, this many of its lanes held
 // candidates in each segment of the current tile: then the any-pass + vote + recompute of the sparse
 // path costs more than building every lane's masks right away.
-constexpr uint32_t kDenseLanes = 6;
+// Measured (profiles/dense_lanes_r02.txt): long patterns gain from the dense path early -- its ONE verification per segment
+// replaces one per slab, and a 25-byte comparison is what costs -- (m = 25 on English prose: 1.50 -> 2.03 TB/s at 3),
+// short ones lose (m = 8: 2.24 -> 1.77 TB/s at 3; DNA m = 7: 1.94 -> 1.51), so the threshold follows the pattern length.
+constexpr uint32_t kDenseLanesLong = 3, kDenseLanesShort = 6;
 
 struct VerifyCtx {
     const uint8_t *vbase, *pat;
@@ -506,20 +514,23 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
         const uint32_t seg_off = warp * WARP_BYTES + sg * kSegBytes;
         const int64_t seg_p0 = tile_v0 + seg_off + lane * 16 + OFFS;
         uint4 w[4];
-        uint32_t w4[4], hm[4], seg_hits = 0;
+        uint32_t w4[4], hm[4];
         load_segment(st + seg_off, lane, w, w4);
-        uint32_t any_cand = 0;
+        // candidate masks of all four slabs, then ONE verification for the lane's whole share of the segment: candidates
+        // of different slabs usually sit in different lanes, and the lanes of one call verify concurrently
+        unsigned long long cand64 = 0;
 #pragma unroll
         for (int sl = 0; sl < 4; ++sl) {
-            const int64_t p0 = seg_p0 + sl * 512;
             uint32_t cand = filter_mask<VARIANT, FLAG>(w[sl], w4[sl], A);
-            if (!vc.all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
-            any_cand |= cand;
-            hm[sl] = 0;
-            if (cand) hm[sl] = vc.exact_filter ? cand : verify_candidates(cand, vc.vbase, p0, A.m, vc.pat, vc.rpat, vc.bad, vc.good, A.verify_smem != 0);
-            seg_hits += __popc(hm[sl]);
+            if (!vc.all_valid) cand &= valid_bits(seg_p0 + sl * 512, A.vmin, A.vmax);
+            cand64 |= (unsigned long long)cand << (16 * sl);
         }
-        cand_lanes += __popc(__ballot_sync(0xFFFFFFFFu, any_cand != 0));
+        cand_lanes += __popc(__ballot_sync(0xFFFFFFFFu, cand64 != 0));
+        if (cand64 && !vc.exact_filter)
+            cand64 = verify_candidates(cand64, vc.vbase, seg_p0, A.m, vc.pat, vc.rpat, vc.bad, vc.good, A.verify_smem != 0);
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) hm[sl] = (uint32_t)(cand64 >> (16 * sl)) & 0xFFFFu;
+        const uint32_t seg_hits = __popcll(cand64);
         const uint32_t hit_lanes = __ballot_sync(0xFFFFFFFFu, seg_hits != 0);
         found += seg_hits;
         if (!POSITIONS && A.find_epoch && hit_lanes) report_first(A, hm, tile_v0 + seg_off + OFFS, lane);
@@ -527,7 +538,7 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
     }
     if (POSITIONS && tile_total && lane == 0)
         atomicAdd(&A.block_sum[(uint32_t)((tile_v0 + warp * WARP_BYTES) / kBlockBytes)], tile_total);
-    return found | (cand_lanes >= kDenseLanes * (WARP_BYTES / kSegBytes) ? (1ull << 63) : 0ull);
+    return found | (cand_lanes >= A.dense_lanes * (WARP_BYTES / kSegBytes) ? (1ull << 63) : 0ull);
 }
 
 template <int VARIANT, int FULL8, int TILE, bool POSITIONS>
@@ -708,20 +719,25 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                         any[sl] = VARIANT == kMulti ? multi_any(w[sl], w4[sl], w5[sl], A.hmul, A.hmul2, M.bits) : filter_any<VARIANT, FULL8>(w[sl], w4[sl], A);
                     const uint32_t vote = __ballot_sync(0xFFFFFFFFu, any[0] | any[1] | any[2] | any[3]);
                     if (vote) {  // warp-uniform and rare: the common path ends at this branch
+                        if (VARIANT == kMulti) {
 #pragma unroll
-                        for (int sl = 0; sl < 4; ++sl) {
-                            if (VARIANT == kMulti) {
+                            for (int sl = 0; sl < 4; ++sl) {
                                 if (any[sl]) {
                                     hm[sl] = multi_chunk(A, M, mblob, w[sl], w4[sl], w5[sl], seg_p0 + sl * 512 - OFFS, vbase);
                                     seg_hits += __popc(hm[sl]);
                                 }
-                            } else if (any[sl]) {
-                                const int64_t p0 = seg_p0 + sl * 512;
-                                uint32_t cand = filter_mask<VARIANT, FULL8>(w[sl], w4[sl], A);
-                                if (!all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
-                                if (cand)
-                                    hm[sl] = exact_filter ? cand : verify_candidates(cand, vbase, p0, A.m, pat, rpat, bad, good, A.verify_smem != 0);
-                                seg_hits += __popc(hm[sl]);
+                            }
+                        } else {
+#pragma unroll
+                            for (int sl = 0; sl < 4; ++sl) {
+                                if (any[sl]) {
+                                    const int64_t p0 = seg_p0 + sl * 512;
+                                    uint32_t cand = filter_mask<VARIANT, FULL8>(w[sl], w4[sl], A);
+                                    if (!all_valid) cand &= valid_bits(p0, A.vmin, A.vmax);
+                                    if (cand)
+                                        hm[sl] = exact_filter ? cand : (uint32_t)verify_candidates(cand, vbase, p0, A.m, pat, rpat, bad, good, A.verify_smem != 0);
+                                    seg_hits += __popc(hm[sl]);
+                                }
                             }
                         }
                         has_hits = __any_sync(0xFFFFFFFFu, seg_hits != 0);
@@ -737,7 +753,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
             }
             if (POSITIONS && tile_total && lane == 0)  // a warp's 4 KiB of a tile lie inside one 2 MiB block
                 atomicAdd(&A.block_sum[(uint32_t)((tile_v0 + warp * WARP_BYTES) / kBlockBytes)], tile_total);
-            dense_mode = cand_lanes >= kDenseLanes * SEGS;  // takes effect with the next tile
+            dense_mode = cand_lanes >= A.dense_lanes * SEGS;  // takes effect with the next tile
         }
         // every lane is done reading the stage: hand it back to the producer
         __syncwarp();
@@ -1407,6 +1423,7 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     a->num_segs = (uint32_t)(tiles * (tile / kSegBytes));
     a->num_blocks = (a->num_segs + kBlockSegs - 1) / kBlockSegs;
     a->owner_offset = (variant == BMX_VARIANT_QGRAM || multi) ? -3 : 0;
+    a->dense_lanes = (uint32_t)std::max(1, std::min(33, env_int("BMX_DENSE_LANES", (int)(m >= 16 ? kDenseLanesLong : kDenseLanesShort))));
     // BMX_SPARE_SMS leaves SMs free for concurrently running kernels (the NCCL collectives of a
     // multi-GPU pipeline cannot start while a persistent grid holds every SM)
     const int spare = std::max(0, std::min(sm_count - 1, env_int("BMX_SPARE_SMS", 0)));
