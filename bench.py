@@ -297,6 +297,66 @@ def measure_config(bmx, torch, name, dev, local, args, peak):
                          "algorithmic_bytes": rf["algorithmic_bytes"], "step_frac": rf["step_frac"]}}
 
 
+def e2e_balanced_leg(bmx, bd, torch, dist, w, pat, plants, total_n, world, rank, local, dev, e2e_cap, e2e_steps, total_hits, old_host):
+    """e2e with shards proportional to each rank's host->device rate, measured with all ranks copying at once.
+    Returns the e2e record, or None when the rates are within 10 % of each other (nothing to balance)."""
+    m = len(pat)
+    alpha = bmx.synth.ALPHABETS[w["alphabet"]]
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
+    probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    probe_d.copy_(probe_h, non_blocking=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0, copied = time.perf_counter(), 0
+    while time.perf_counter() - t0 < 0.25:          # every rank copies for the same 250 ms: all links busy throughout
+        probe_d.copy_(probe_h, non_blocking=True)
+        torch.cuda.synchronize()
+        copied += probe_h.numel()
+    rate = copied / (time.perf_counter() - t0)
+    rates = torch.zeros(world, dtype=torch.float64, device=dev)
+    rates[rank] = rate
+    dist.all_reduce(rates)
+    rates = rates.cpu().tolist()
+    del probe_h, probe_d
+    if max(rates) < 1.10 * min(rates) and not os.environ.get("BMX_BENCH_FORCE_BALANCE"):   # (test knob)
+        return None
+    # rank r owns the start positions [cut[r], cut[r+1]) of the same global text; cuts are 16-byte aligned
+    total_rate, acc, cut = sum(rates), 0.0, [0]
+    for r in range(world - 1):
+        acc += rates[r]
+        cut.append(min(total_n, int(total_n * acc / total_rate) // 16 * 16))
+    cut.append(total_n)
+    lo2, hi2 = cut[rank], cut[rank + 1]
+    end2 = min(total_n, hi2 + m - 1)
+    shard = torch.empty(end2 - lo2, dtype=torch.uint8, device=dev)
+    bmx.synth.fill_device(shard, lo2, w["seed"], alpha)
+    bmx.synth.plant_device(shard, pat, plants[(plants + m > lo2) & (plants < end2)], base=lo2)
+    if old_host is not None and old_host.numel() >= end2 - lo2:
+        host = old_host[: end2 - lo2]              # the equal-shard buffer is big enough: no second pinned allocation
+    else:
+        del old_host
+        host = torch.empty(end2 - lo2, dtype=torch.uint8, pin_memory=True)
+    host.copy_(shard)
+    torch.cuda.synchronize()
+    del shard
+    bmx.search(host, pat, max_positions=e2e_cap, device=local)          # warm-up (buffers grow to the new shard size)
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        c2, p2 = bmx.search(host, pat, max_positions=e2e_cap, device=local)
+        tot, _, _ = bd.combine_hits(c2, torch.from_numpy(p2 + lo2).to(dev), group=None, device=dev)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if int(tot) != int(total_hits):
+        raise RuntimeError(f"balanced shards found {tot} hits, the device-resident run {total_hits}")
+    return {"value": total_n / (float(dt.item()) / e2e_steps) / 1e9, "unit": "GB/s", "steps": e2e_steps,
+            "h2d_bytes_per_step": int(end2 - lo2) + m + 1024 + 4 * m, "d2h_bytes_per_step": 8 * int(min(c2, e2e_cap)) + 8,
+            "api": "bmx_search_ex (host pointers, pinned text)",
+            "shards": "proportional to each rank's host->device rate, all ranks copying at once",
+            "rank_rates_gbs": [round(x / 1e9, 1) for x in rates], "rank0_shard_bytes": int(cut[1] - cut[0])}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -520,6 +580,22 @@ def run_ours(args):
         c2, e2e = e2e_run(host_text, "pinned")
         ok = ok and c2 == count
         host_sample = host_text
+        # N > 1: the GPUs of a box need not ingest at the same rate (8-GPU boxes of this pool: 23 GB/s per GPU on one half,
+        # 35 on the other when all eight copy at once, profiles/ingest_topology_r02.txt), and equal shards finish with
+        # the slowest link.  Second leg: the SAME global text cut in proportion to each rank's measured host->device rate.
+        if world > 1 and not args.no_balance:
+            try:
+                old_host, host_text, host_sample = host_text, None, None     # the leg reuses or replaces the pinned buffer
+                bal = e2e_balanced_leg(bmx, bd, torch, dist, w, pat, plants, total_n, world, rank, local, dev, e2e_cap, e2e_steps, total_hits, old_host)
+                del old_host
+            except Exception as exc:   # noqa: BLE001 -- the equal-shard figure stands
+                print(f"[rank {rank}] balanced e2e leg failed: {exc!r}", file=sys.stderr, flush=True)
+                bal = None
+            flag = torch.tensor([1 if bal is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) and bal["value"] > e2e["value"]:
+                bal["equal_shards"] = {"value": e2e["value"], "unit": "GB/s"}
+                e2e = bal
         if world == 1 and not args.no_pageable:
             pageable = host_text.numpy().copy()
             c3, e2e_pageable = e2e_run(pageable, "pageable")
@@ -691,6 +767,7 @@ def main():
     ap.add_argument("--no-configs", action="store_true", help="N = 1: skip the other BASELINE configs")
     ap.add_argument("--no-pageable", action="store_true", help="N = 1: skip the pageable-text e2e leg")
     ap.add_argument("--no-numa-bind", action="store_true")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: skip the e2e leg with shards proportional to the ranks' ingest rates")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="N > 1: exchange step over peer memory (library) or NCCL all-gather")
     ap.add_argument("--cpu-sample-bytes", type=int, default=4 * GIB)
     args = ap.parse_args()
