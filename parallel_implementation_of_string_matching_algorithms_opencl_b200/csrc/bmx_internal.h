@@ -55,6 +55,7 @@ struct ScanArgs {
     uint32_t verify_smem;   // 1: candidates are verified from the staged tile, 0: from global
     uint32_t dense_lanes;   // a warp whose segments held candidates in this many lanes on average builds all masks right away
     uint32_t pat_smem;      // 1: pattern + tables copied to shared memory
+    uint32_t coop_verify;   // 1: flagged chunks are checked by the whole warp (coop_verify16), 0: by their own lane with BM skips
     // filter constants
     uint32_t f[4];          // QGRAM: hash of P[r..r+q) for r = 0..3; WINDOW: f[0] = target
     uint32_t hmul;          // QGRAM: hash multiplier K << (32 - 8*(q-4)); the shift drops the bytes beyond the q-gram

@@ -209,6 +209,77 @@ __device__ __noinline__ unsigned long long verify_candidates(unsigned long long 
     return hits;
 }
 
+// Warp-cooperative exact check of the 16 start positions owned by one 16-byte chunk -- what the sparse path does with
+// a chunk the filter flagged.  The walk above is one lane following the reference's loop while 31 lanes wait, a chain
+// of dependent shared-memory loads per candidate; here the whole warp looks at the chunk at once: lane i compares
+// pattern word (i >> 4) at start position (i & 15), one ballot keeps the positions whose first 8 bytes match, and each
+// survivor (almost always a true occurrence) has the rest of its pattern compared 32 words = 128 bytes per step.  The
+// result is the same set the reference's loop reports -- it advances by one after a match (kernel1.cl:24), so every
+// occurrence is reported; the skips only prune non-matches.
+// Everything that depends only on the lane is computed once per kernel (CoopLane): a chunk starts on a 16-byte
+// boundary, so the aligned word a lane reads, its funnel shift and its (masked) pattern word never change.
+struct CoopLane {
+    int32_t off1;     // phase 1: byte offset (multiple of 4, may be -4) of the lane's aligned word pair from the chunk
+    uint32_t sh1;     //          funnel shift in bits
+    uint32_t pw1, pm1;  //        pattern word (lane >> 4) and its byte mask (0: the pattern has no such word)
+    uint32_t pw2, pm2;  // phase 2, first round: pattern word 2 + lane and its byte mask
+    int32_t nwords;
+};
+__device__ __forceinline__ uint32_t pat_word_mask(int32_t wi, int32_t m)
+{
+    const int32_t left = m - 4 * wi;   // pattern bytes in word wi
+    return left >= 4 ? 0xFFFFFFFFu : (left <= 0 ? 0u : (0xFFFFFFFFu >> (32 - 8 * left)));
+}
+template <int OFFS>
+__device__ __forceinline__ CoopLane coop_lane_setup(const uint32_t *patw, int32_t m, int lane)
+{
+    CoopLane c;
+    const int32_t o1 = OFFS + (lane & 15) + 4 * (lane >> 4);
+    c.off1 = o1 & ~3;
+    c.sh1 = 8u * (uint32_t)(o1 & 3);
+    c.nwords = (m + 3) >> 2;
+    c.pm1 = pat_word_mask(lane >> 4, m);
+    c.pw1 = c.pm1 ? patw[lane >> 4] & c.pm1 : 0u;
+    c.pm2 = pat_word_mask(2 + lane, m);
+    c.pw2 = c.pm2 ? patw[2 + lane] & c.pm2 : 0u;
+    return c;
+}
+// cp: first byte of the chunk in the staged tile (16-byte aligned).  Returns the hit bits of the chunk (bit b = start
+// position cp + OFFS + b).
+template <int OFFS>
+__device__ __forceinline__ uint32_t coop_verify16(const uint8_t *cp, const CoopLane &c, const uint32_t *patw, int32_t m, int lane)
+{
+    const uint32_t *w1 = reinterpret_cast<const uint32_t *>(cp + c.off1);
+    const uint32_t x1 = __funnelshift_r(w1[0], w1[1], c.sh1);
+    const uint32_t b = __ballot_sync(0xFFFFFFFFu, ((x1 ^ c.pw1) & c.pm1) == 0u);
+    uint32_t alive = b & (b >> 16);
+    if (c.nwords > 2) {
+        uint32_t left = alive;
+        while (left) {
+            const int32_t bit = __ffs(left) - 1;
+            left &= left - 1;
+            // word 2 + lane of the pattern at start position OFFS + bit: the alignment is the same for all lanes
+            const int32_t o2 = OFFS + bit + 8;
+            const uint32_t *w2 = reinterpret_cast<const uint32_t *>(cp + (o2 & ~3)) + lane;
+            const uint32_t sh2 = 8u * (uint32_t)(o2 & 3);
+            // (lanes beyond the pattern's last word load nothing: their words may lie behind the staged halo)
+            uint32_t x2 = 0u;
+            if (c.pm2) x2 = __funnelshift_r(w2[0], w2[1], sh2);
+            bool same = __all_sync(0xFFFFFFFFu, ((x2 ^ c.pw2) & c.pm2) == 0u);
+            for (int32_t w0 = 34; w0 < c.nwords && same; w0 += 32) {   // patterns longer than 136 bytes
+                const int32_t wi = w0 + lane;
+                const uint32_t pm = pat_word_mask(wi, m);
+                const uint32_t pw = pm ? patw[wi] & pm : 0u;
+                uint32_t x = 0u;
+                if (pm) x = __funnelshift_r(w2[w0 - 2], w2[w0 - 1], sh2);
+                same = __all_sync(0xFFFFFFFFu, ((x ^ pw) & pm) == 0u);
+            }
+            if (!same) alive &= ~(1u << bit);
+        }
+    }
+    return alive;
+}
+
 // Bits b (0..15) whose start position p0 + b lies in [vmin, vmax].
 __device__ __forceinline__ uint32_t valid_bits(int64_t p0, int64_t vmin, int64_t vmax)
 {
@@ -664,6 +735,12 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     const int32_t *good = A.pat_smem ? ctl->good : A.g_good;
     const uint32_t *rpat = A.pat_smem ? ctl->rpat : nullptr;
     const bool exact_filter = (VARIANT == kShiftAnd) || (VARIANT == kWindow && A.m <= 4);
+    // flagged chunks are checked by the whole warp when pattern and window both sit in shared memory (m <= kPatSmemMax)
+    constexpr bool kNeverVerifies = (VARIANT == kShiftAnd) || (VARIANT == kWindow && FULL8 >= 2);   // m <= 3: the filter is exact
+    const bool coop = !kNeverVerifies && !exact_filter && A.pat_smem != 0u && A.verify_smem != 0u && A.coop_verify != 0u;
+    const uint32_t *patw = reinterpret_cast<const uint32_t *>(ctl->pat);
+    CoopLane cl{};
+    if (coop) cl = coop_lane_setup<OFFS>(patw, A.m, lane);
     unsigned long long my_count = 0;  // count-only mode
     bool dense_mode = false;          // per warp: candidates in most lanes -> next tile takes dense_tile()
 
@@ -691,7 +768,11 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         }
         if (!took_dense) {
             uint32_t cand_lanes = 0, tile_total = 0;
+#ifdef BMX_SEG_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
             for (int sg = 0; sg < SEGS; ++sg) {
                 uint32_t hm[4] = {0u, 0u, 0u, 0u};
                 uint32_t seg_hits = 0;
@@ -726,6 +807,21 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                                     hm[sl] = multi_chunk(A, M, mblob, w[sl], w4[sl], w5[sl], seg_p0 + sl * 512 - OFFS, vbase);
                                     seg_hits += __popc(hm[sl]);
                                 }
+                            }
+                        } else if (coop) {
+                            // flagged chunks one after the other, each checked by the whole warp (coop_verify16)
+#pragma unroll
+                            for (int sl = 0; sl < 4; ++sl) {
+                                uint32_t flagged = __ballot_sync(0xFFFFFFFFu, any[sl]);
+                                while (flagged) {
+                                    const int src = __ffs(flagged) - 1;
+                                    flagged &= flagged - 1;
+                                    const int32_t rel = (int32_t)seg_off + sl * 512 + src * 16;
+                                    uint32_t h16 = coop_verify16<OFFS>(st + rel, cl, patw, A.m, lane);
+                                    if (!all_valid && h16) h16 &= valid_bits(tile_v0 + rel + OFFS, A.vmin, A.vmax);
+                                    if (lane == src) hm[sl] = h16;
+                                }
+                                seg_hits += __popc(hm[sl]);
                             }
                         } else {
 #pragma unroll
@@ -1423,7 +1519,12 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     a->num_segs = (uint32_t)(tiles * (tile / kSegBytes));
     a->num_blocks = (a->num_segs + kBlockSegs - 1) / kBlockSegs;
     a->owner_offset = (variant == BMX_VARIANT_QGRAM || multi) ? -3 : 0;
-    a->dense_lanes = (uint32_t)std::max(1, std::min(33, env_int("BMX_DENSE_LANES", (int)(m >= 16 ? kDenseLanesLong : kDenseLanesShort))));
+    a->coop_verify = env_int("BMX_COOP_VERIFY", 1) != 0 ? 1u : 0u;   // measurement knob
+    // Patterns whose flagged chunks are checked by the whole warp never gain from the dense path (profiles/verify_ab_r02.txt:
+    // equal or faster at every density measured): 33 lanes = never.
+    const bool verifies = !(variant == BMX_VARIANT_SHIFTAND || (variant == BMX_VARIANT_WINDOW && m <= 4));
+    const bool coop = verifies && a->coop_verify && a->pat_smem && a->verify_smem;
+    a->dense_lanes = (uint32_t)std::max(1, std::min(33, env_int("BMX_DENSE_LANES", coop ? 33 : (int)(m >= 16 ? kDenseLanesLong : kDenseLanesShort))));
     // BMX_SPARE_SMS leaves SMs free for concurrently running kernels (the NCCL collectives of a
     // multi-GPU pipeline cannot start while a persistent grid holds every SM)
     const int spare = std::max(0, std::min(sm_count - 1, env_int("BMX_SPARE_SMS", 0)));
