@@ -619,6 +619,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     constexpr int OFFS = (VARIANT == kQgram || VARIANT == kMulti) ? -3 : 0;    // start position of bit 0 relative to the chunk
     constexpr int SEGS = WARP_BYTES / kSegBytes;        // 2 KiB segments per warp per tile
     static_assert(SEGS >= 1 && SEGS * kSegBytes * kConsumerWarps == TILE, "tile must be a multiple of 16 KiB");
+    constexpr int kSegUnroll = (VARIANT == kWindow && FULL8 == 1) ? 1 : SEGS;
 
     extern __shared__ __align__(128) uint8_t smem[];
     SmemCtl *ctl = reinterpret_cast<SmemCtl *>(smem);
@@ -768,11 +769,9 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         }
         if (!took_dense) {
             uint32_t cand_lanes = 0, tile_total = 0;
-#ifdef BMX_SEG_ROLLED
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
+            // (the 4-byte WINDOW kernel is ALU-bound and its two unrolled segments gave the compiler nothing to overlap: one
+            // rolled copy measured +5 % on bytes256 m = 4; every other kernel is faster unrolled)
+#pragma unroll(kSegUnroll)
             for (int sg = 0; sg < SEGS; ++sg) {
                 uint32_t hm[4] = {0u, 0u, 0u, 0u};
                 uint32_t seg_hits = 0;

@@ -805,3 +805,49 @@ def test_single_process_multi_gpu_entry_point(bmx, oracle, dev):
         assert count == want.size and pos.size == 0
         assert mg.search(b"ab", b"abc")[0] == 0
         mg.close()
+
+
+def test_cooperative_verification_edges(bmx, oracle, dev, monkeypatch):
+    """The sparse path's flagged chunks are checked by the whole warp (coop_verify16): pattern lengths around its
+    word and round boundaries (8 bytes per ballot; 128 bytes per survivor step; the shared-memory pattern limit),
+    candidates that share their first 8 bytes with the pattern and differ later, occurrences at both ends of the
+    text and across tile seams, overlapping occurrences, and periodic texts where every chunk is flagged.  The
+    lane-walk with BM skips (BMX_COOP_VERIFY=0) must give the same list."""
+    rng = np.random.default_rng(4242)
+    n = (3 << 20) + 77
+    base = rng.integers(0, 4, size=n, dtype=np.uint8) + 65                 # ACGT-like: false candidates galore
+    for m in (5, 6, 7, 8, 9, 11, 12, 13, 31, 32, 33, 36, 37, 135, 136, 137, 140, 141, 264, 265, 300, 1023, 1024):
+        text = base.copy()
+        o = int(rng.integers(1000, n // 2))
+        pat = text[o:o + m].tobytes()
+        near = bytearray(pat)
+        near[-1] ^= 1                                                       # differs in the last byte only
+        mid = bytearray(pat)
+        mid[min(m - 1, 8)] ^= 1                                             # differs right behind the first 8 bytes
+        spots = [0, 32768 - m + 3, 32768 - 2, 65536 - 1, (1 << 20) + 5, n - m]    # text ends, tile seams
+        for k, s in enumerate(spots):
+            text[s:s + m] = np.frombuffer(pat, dtype=np.uint8)
+            d = s + 3 * m + 64 + k
+            if d + m < n - m - 64:
+                text[d:d + m] = np.frombuffer(bytes(near if k % 2 else mid), dtype=np.uint8)
+        if m <= 300:                                                        # overlapping copies of a periodic pattern
+            text[200000:200000 + 5 * m] = np.frombuffer((pat[: max(1, m // 3)] * (5 * m))[: 5 * m], dtype=np.uint8)
+        want = oracle.search_np(text, pat, threads=-1)
+        assert want.size >= 4                                               # (neighbouring spots may overwrite each other)
+        for misalign in (0, 5):
+            td = to_dev(text, dev, misalign=misalign)
+            for coop in ("1", "0"):
+                monkeypatch.setenv("BMX_COOP_VERIFY", coop)
+                count, got, _ = gpu_positions(bmx, td, pat, cap=want.size + 8)
+                assert count == want.size and np.array_equal(got, want), (m, misalign, coop)
+                count, _, _ = bmx.search_device(td, pat)
+                assert count == want.size, (m, misalign, coop, "count-only")
+    monkeypatch.delenv("BMX_COOP_VERIFY")
+    # every chunk of every segment flagged: 'ab' * k searched for (ab)^4 and (ab)^20, and one byte off
+    per = np.frombuffer((b"ab" * (1 << 19)), dtype=np.uint8).copy()
+    per[777777] = ord("c")
+    td = to_dev(per, dev, misalign=1)
+    for pat in (b"abababab", b"ab" * 20, b"babababa" + b"b"):
+        want = oracle.search_np(per, pat, threads=-1)
+        count, got, _ = gpu_positions(bmx, td, pat, cap=want.size + 1)
+        assert count == want.size and np.array_equal(got, want), pat
