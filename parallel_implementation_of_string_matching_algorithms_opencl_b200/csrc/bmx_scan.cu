@@ -961,6 +961,7 @@ constexpr int kExpandWarps = kExpandThreads / 32;
 constexpr uint32_t kStageThreshold = 96;  // segments with more hits go through shared memory
 constexpr uint32_t kSoloMaxHits = 64;     // segments with at most this many hits are expanded by a single lane
 constexpr uint32_t kFlatMaxHits = 1024;   // items (16 segments) with at most this many hits are expanded flat
+constexpr int kSparseSegs = 3;            // items with at most this many segments holding hits read only those segments
 
 // Warp-cooperative store of out[0..limit) = value(r) with 16-byte vector stores: lane l writes the
 // element pairs (2l, 2l+1) + 64j of the 16-byte aligned middle part, one lane each the ragged ends.
@@ -1095,6 +1096,38 @@ __device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, un
     // one warp scan over the lanes' popcounts ranks every lane inside the item, and each lane stores its own
     // hits.  No per-segment scans, all 32 lanes busy: a fifth of the instructions of the paths below.
     const uint32_t item_total = __shfl_sync(0xFFFFFFFFu, incl, kItemSegs - 1);
+    // Sparse items (the usual case of a sparse text: one or two of the 16 segments hold a hit or a few): only those
+    // segments are read -- lane l takes the 64 start positions 64 l .. 64 l + 63 of the segment as ONE 8-byte load, a
+    // warp scan ranks the lanes, every lane stores its own hits.  ~70 warp-instructions per such segment where the flat
+    // path below spends ~400 on the item (profiles/r02_ncu_expand_dna8.txt: 425 instructions per hit on DNA, m = 8).
+    const uint32_t seg_vote = __ballot_sync(0xFFFFFFFFu, c != 0u);
+    if (share == 1 && __popc(seg_vote) <= kSparseSegs && item_total <= kStageThreshold) {   // (few hits: no full segments either)
+        for (uint32_t v = seg_vote; v; v &= v - 1) {
+            const int src = __ffs(v) - 1;
+            const uint32_t seg = seg0 + (uint32_t)src;
+            const unsigned long long seg_rank = item_rank + __shfl_sync(0xFFFFFFFFu, incl - c, src);
+            const uint2 mk = reinterpret_cast<const uint2 *>(A.mask16 + (size_t)seg * kSegChunks)[lane];
+            const uint32_t mine = __popc(mk.x) + __popc(mk.y);
+            uint32_t upto = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, upto, o);
+                if (lane >= o) upto += t;
+            }
+            const unsigned long long rank = seg_rank + (upto - mine);
+            const int64_t room = A.pos_cap - (int64_t)rank;   // truncated output keeps the smallest positions
+            if (mine != 0u && room > 0) {
+                int64_t *out = A.pos_out + rank;
+                const int64_t pos0 = (int64_t)seg * kSegBytes + A.owner_offset + A.pos_bias + lane * 64;
+                uint32_t written = 0;
+                for (uint32_t w = mk.x; w; w &= w - 1, ++written)
+                    if ((int64_t)written < room) out[written] = pos0 + (__ffs(w) - 1);
+                for (uint32_t w = mk.y; w; w &= w - 1, ++written)
+                    if ((int64_t)written < room) out[written] = pos0 + 32 + (__ffs(w) - 1);
+            }
+        }
+        return;
+    }
     if (share == 1 && item_total <= kFlatMaxHits) {
         const uint32_t cs = __shfl_sync(0xFFFFFFFFu, c, lane >> 1);   // hits of the segment this lane's masks belong to
         uint4 v[8];
