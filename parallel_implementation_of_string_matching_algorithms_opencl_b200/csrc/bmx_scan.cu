@@ -211,19 +211,20 @@ __device__ __noinline__ unsigned long long verify_candidates(unsigned long long 
 
 // Warp-cooperative exact check of the 16 start positions owned by one 16-byte chunk -- what the sparse path does with
 // a chunk the filter flagged.  The walk above is one lane following the reference's loop while 31 lanes wait, a chain
-// of dependent shared-memory loads per candidate; here the whole warp looks at the chunk at once: lane i compares
-// pattern word (i >> 4) at start position (i & 15), one ballot keeps the positions whose first 8 bytes match, and each
-// survivor (almost always a true occurrence) has the rest of its pattern compared 32 words = 128 bytes per step.  The
-// result is the same set the reference's loop reports -- it advances by one after a match (kernel1.cl:24), so every
-// occurrence is reported; the skips only prune non-matches.
+// of dependent shared-memory loads per candidate; here the whole warp looks at the chunk at once: lane i compares one
+// of the pattern's LAST two words at start position (i & 15) -- the filter's q-gram sits at the pattern's front, so the
+// tail is what tells "occurrences starting from" from "occurrences by process" --, one ballot keeps the positions whose
+// last 8 bytes match, and each survivor (almost always a true occurrence) has the words in front compared 32 words =
+// 128 bytes per step.  The result is the same set the reference's loop reports -- it advances by one after a match
+// (kernel1.cl:24), so every occurrence is reported; the skips only prune non-matches.
 // Everything that depends only on the lane is computed once per kernel (CoopLane): a chunk starts on a 16-byte
 // boundary, so the aligned word a lane reads, its funnel shift and its (masked) pattern word never change.
 struct CoopLane {
     int32_t off1;     // phase 1: byte offset (multiple of 4, may be -4) of the lane's aligned word pair from the chunk
     uint32_t sh1;     //          funnel shift in bits
-    uint32_t pw1, pm1;  //        pattern word (lane >> 4) and its byte mask (0: the pattern has no such word)
-    uint32_t pw2, pm2;  // phase 2, first round: pattern word 2 + lane and its byte mask
-    int32_t nwords;
+    uint32_t pw1, pm1;  //        the lane's pattern word (one of the last two) and its byte mask (0: the pattern has no such word)
+    uint32_t pw2, pm2;  // phase 2, first round: pattern word `lane` (in front of the last two) and its mask
+    int32_t nwords, front;   // pattern words; words in front of the last two
 };
 __device__ __forceinline__ uint32_t pat_word_mask(int32_t wi, int32_t m)
 {
@@ -234,45 +235,48 @@ template <int OFFS>
 __device__ __forceinline__ CoopLane coop_lane_setup(const uint32_t *patw, int32_t m, int lane)
 {
     CoopLane c;
-    const int32_t o1 = OFFS + (lane & 15) + 4 * (lane >> 4);
+    c.nwords = (m + 3) >> 2;
+    c.front = c.nwords > 2 ? c.nwords - 2 : 0;
+    const int32_t w1 = c.front + (lane >> 4);
+    const int32_t o1 = OFFS + (lane & 15) + 4 * w1;
     c.off1 = o1 & ~3;
     c.sh1 = 8u * (uint32_t)(o1 & 3);
-    c.nwords = (m + 3) >> 2;
-    c.pm1 = pat_word_mask(lane >> 4, m);
-    c.pw1 = c.pm1 ? patw[lane >> 4] & c.pm1 : 0u;
-    c.pm2 = pat_word_mask(2 + lane, m);
-    c.pw2 = c.pm2 ? patw[2 + lane] & c.pm2 : 0u;
+    c.pm1 = pat_word_mask(w1, m);
+    c.pw1 = c.pm1 ? patw[w1] & c.pm1 : 0u;
+    c.pm2 = lane < c.front ? 0xFFFFFFFFu : 0u;
+    c.pw2 = c.pm2 ? patw[lane] : 0u;
     return c;
 }
 // cp: first byte of the chunk in the staged tile (16-byte aligned).  Returns the hit bits of the chunk (bit b = start
 // position cp + OFFS + b).
 template <int OFFS>
-__device__ __forceinline__ uint32_t coop_verify16(const uint8_t *cp, const CoopLane &c, const uint32_t *patw, int32_t m, int lane)
+__device__ __forceinline__ uint32_t coop_verify16(const uint8_t *cp, const CoopLane &c, const uint32_t *patw, int lane)
 {
     const uint32_t *w1 = reinterpret_cast<const uint32_t *>(cp + c.off1);
     const uint32_t x1 = __funnelshift_r(w1[0], w1[1], c.sh1);
     const uint32_t b = __ballot_sync(0xFFFFFFFFu, ((x1 ^ c.pw1) & c.pm1) == 0u);
     uint32_t alive = b & (b >> 16);
-    if (c.nwords > 2) {
+    if (c.front > 0) {
         uint32_t left = alive;
         while (left) {
             const int32_t bit = __ffs(left) - 1;
             left &= left - 1;
-            // word 2 + lane of the pattern at start position OFFS + bit: the alignment is the same for all lanes
-            const int32_t o2 = OFFS + bit + 8;
+            // word `lane` of the pattern at start position OFFS + bit: the alignment is the same for all lanes
+            const int32_t o2 = OFFS + bit;
             const uint32_t *w2 = reinterpret_cast<const uint32_t *>(cp + (o2 & ~3)) + lane;
             const uint32_t sh2 = 8u * (uint32_t)(o2 & 3);
-            // (lanes beyond the pattern's last word load nothing: their words may lie behind the staged halo)
+            // (lanes beyond the pattern's words load nothing: their words may lie behind the staged halo)
             uint32_t x2 = 0u;
             if (c.pm2) x2 = __funnelshift_r(w2[0], w2[1], sh2);
             bool same = __all_sync(0xFFFFFFFFu, ((x2 ^ c.pw2) & c.pm2) == 0u);
-            for (int32_t w0 = 34; w0 < c.nwords && same; w0 += 32) {   // patterns longer than 136 bytes
+            for (int32_t w0 = 32; w0 < c.front && same; w0 += 32) {   // patterns longer than 136 bytes
                 const int32_t wi = w0 + lane;
-                const uint32_t pm = pat_word_mask(wi, m);
-                const uint32_t pw = pm ? patw[wi] & pm : 0u;
-                uint32_t x = 0u;
-                if (pm) x = __funnelshift_r(w2[w0 - 2], w2[w0 - 1], sh2);
-                same = __all_sync(0xFFFFFFFFu, ((x ^ pw) & pm) == 0u);
+                uint32_t x = 0u, pw = 0u;
+                if (wi < c.front) {
+                    x = __funnelshift_r(w2[w0], w2[w0 + 1], sh2);
+                    pw = patw[wi];
+                }
+                same = __all_sync(0xFFFFFFFFu, x == pw);
             }
             if (!same) alive &= ~(1u << bit);
         }
@@ -816,7 +820,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                                     const int src = __ffs(flagged) - 1;
                                     flagged &= flagged - 1;
                                     const int32_t rel = (int32_t)seg_off + sl * 512 + src * 16;
-                                    uint32_t h16 = coop_verify16<OFFS>(st + rel, cl, patw, A.m, lane);
+                                    uint32_t h16 = coop_verify16<OFFS>(st + rel, cl, patw, lane);
                                     if (!all_valid && h16) h16 &= valid_bits(tile_v0 + rel + OFFS, A.vmin, A.vmax);
                                     if (lane == src) hm[sl] = h16;
                                 }
