@@ -578,8 +578,8 @@ struct VerifyCtx {
 // line so the common path of scan_kernel stays exactly the sparse filter loop.  Returns the hits
 // found (count-only mode adds them up) with bit 63 set while the text is still dense.
 template <int VARIANT, int FLAG, int TILE, bool POSITIONS>
-__device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const uint8_t *st, int64_t tile_v0,
-                                                      VerifyCtx vc, int warp, int lane)
+__device__ __forceinline__ unsigned long long dense_tile_body(const ScanArgs &A, const uint8_t *st, int64_t tile_v0,
+                                                              VerifyCtx vc, int warp, int lane)
 {
     constexpr int WARP_BYTES = TILE / kConsumerWarps;
     constexpr int OFFS = (VARIANT == kQgram || VARIANT == kMulti) ? -3 : 0;
@@ -614,6 +614,16 @@ __device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const u
     if (POSITIONS && tile_total && lane == 0)
         atomicAdd(&A.block_sum[(uint32_t)((tile_v0 + warp * WARP_BYTES) / kBlockBytes)], tile_total);
     return found | (cand_lanes >= A.dense_lanes * (WARP_BYTES / kSegBytes) ? (1ull << 63) : 0ull);
+}
+// Out of line for the kernels that verify (their common path must stay exactly the sparse filter loop); the m = 1 and
+// m = 2 kernels, whose filter is exact and whose dense path is the one natural-language text lives in, inline the body:
+// out of line the kernel arguments are reached through a generic pointer (LD.E, a long-scoreboard stall per segment:
+// profiles/r02_ncu_scan_eng_is.txt), inline they are constant-bank operands ('is' on English prose count-only 4.52 ->
+// 4.86 TB/s, ' ' 5.25 -> 5.78).  m = 3 stays out of line: inlined, its SPARSE path lost 7 % (bytes256: 6.6 -> 5.95 TB/s).
+template <int VARIANT, int FLAG, int TILE, bool POSITIONS>
+__device__ __noinline__ unsigned long long dense_tile(const ScanArgs &A, const uint8_t *st, int64_t tile_v0, VerifyCtx vc, int warp, int lane)
+{
+    return dense_tile_body<VARIANT, FLAG, TILE, POSITIONS>(A, st, tile_v0, vc, warp, lane);
 }
 
 template <int VARIANT, int FULL8, int TILE, bool POSITIONS>
@@ -765,7 +775,9 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         if constexpr (VARIANT != kShiftAnd && VARIANT != kMulti) {
             if (dense_mode) {
                 const VerifyCtx vc{vbase, pat, rpat, bad, good, exact_filter, all_valid};
-                const unsigned long long r = dense_tile<VARIANT, FULL8, TILE, POSITIONS>(A, st, tile_v0, vc, warp, lane);
+                unsigned long long r;
+                if constexpr (VARIANT == kWindow && (FULL8 == 2 || FULL8 == 3)) r = dense_tile_body<VARIANT, FULL8, TILE, POSITIONS>(A, st, tile_v0, vc, warp, lane);
+                else r = dense_tile<VARIANT, FULL8, TILE, POSITIONS>(A, st, tile_v0, vc, warp, lane);
                 dense_mode = (r >> 63) != 0;
                 if (!POSITIONS) my_count += r & ~(1ull << 63);
                 took_dense = true;
@@ -1155,22 +1167,35 @@ __device__ __forceinline__ void expand_item(const ScanArgs &A, uint32_t item, un
         const unsigned long long rank = item_rank + before_me;
         const int64_t room = A.pos_cap - (int64_t)rank;
         if (mine != 0 && room > 0) {
+            // One loop per lane over its HITS: the warp runs max over lanes of `mine` iterations.  Walking the 32 words
+            // of a lane in an unrolled loop with a hit loop inside each (the first version) made the warp pay every
+            // word's worst lane: 1600 instructions per item on English prose (profiles/r02_ncu_expand_eng_is.txt).  The
+            // lane parks its words in shared memory ([word][lane]: its own bank, whatever word each lane is at) and
+            // keeps a bitmap of the nonzero ones, so "next word" is FFS + one LDS and empty words cost nothing.
             int64_t *out = A.pos_out + rank;
             const int64_t pos0 = (int64_t)seg0 * kSegBytes + A.owner_offset + A.pos_bias + lane * 1024;
-            uint32_t written = 0;
+            uint32_t *park = reinterpret_cast<uint32_t *>(stg) + lane;
+            uint32_t nz = 0u;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 const uint32_t ws[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    uint32_t w = ws[j];  // two consecutive 16-bit masks = 32 consecutive start positions
-                    while (w) {
-                        const uint32_t b = __ffs(w) - 1;
-                        w &= w - 1;
-                        if ((int64_t)written < room) out[written] = pos0 + (u * 4 + j) * 32 + b;
-                        ++written;
-                    }
+                for (int k = 0; k < 4; ++k) {
+                    park[(u * 4 + k) * 32] = ws[k];
+                    nz |= ws[k] ? 1u << (u * 4 + k) : 0u;
                 }
+            }
+            uint32_t j = 0, w = 0u, written = 0;
+            for (uint32_t left = mine; left; --left) {
+                if (w == 0u) {   // the parked word behind bit j of nz is nonzero: one reload always suffices
+                    j = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    w = park[j * 32];
+                }
+                const uint32_t b = __ffs(w) - 1;
+                w &= w - 1;
+                if ((int64_t)written < room) out[written] = pos0 + j * 32 + b;
+                ++written;
             }
         }
         return;
