@@ -50,7 +50,14 @@ WORKLOADS = {
     "bytes256_m16_4GiB": dict(alphabet="bytes256", n=4 * GIB, m=16, seed=45, plants=1000, pattern="random"),
     "bytes256_m128_4GiB": dict(alphabet="bytes256", n=4 * GIB, m=128, seed=46, plants=1000, pattern="random"),
     "aaa_1GiB": dict(alphabet="a", n=1 * GIB, m=3, seed=1, plants=0, pattern="aaa"),
+    # not BASELINE configs: the reference's own kind of input at scale (its English fixture input5L.txt, from
+    # tests/golden/golden.npz, tiled to 1 GiB; its own query "is" and a phrase of its console output) and the weakest
+    # sparse case (short pattern, 4-letter alphabet).  Reported in `configs` with "baseline_config": false.
+    "english_is_1GiB": dict(alphabet="english", n=1 * GIB, m=2, seed=0, plants=0, pattern="is"),
+    "english_m25_1GiB": dict(alphabet="english", n=1 * GIB, m=25, seed=0, plants=0, pattern="occurrences starting from"),
+    "dna_m8_1GiB": dict(alphabet="dna", n=1 * GIB, m=8, seed=4321, plants=100, pattern="random"),
 }
+EXTRA_CONFIGS = ("english_is_1GiB", "english_m25_1GiB", "dna_m8_1GiB")
 
 
 def peaks():
@@ -218,6 +225,14 @@ def build_workload(bmx, torch, name, world, rank, dev, bytes_per_gpu=0):
     w = dict(WORKLOADS[name])
     if bytes_per_gpu:
         w["n"] = bytes_per_gpu
+    if w["alphabet"] == "english":      # single GPU only: the reference's fixture tiled
+        z = np.load(ROOT / "tests" / "golden" / "golden.npz")
+        base = np.asarray(z["text/input5L"], dtype=np.uint8)
+        n = w["n"]
+        text = torch.from_numpy(np.tile(base, n // base.size + 1)[:n].copy()).to(dev)
+        pat = w["pattern"].encode()
+        return dict(name=name, w=w, m=len(pat), total_n=n, lo=0, end=n, pat=pat, plants=np.zeros(0, dtype=np.int64), text=text,
+                    dense=False, cap=n // 8)
     alpha = bmx.synth.ALPHABETS[w["alphabet"]]
     m = w["m"]
     total_n = w["n"] * world
@@ -629,6 +644,12 @@ def run_ours(args):
                           "roofline": {k: rf[k] for k in ("frac", "achieved", "kernel", "kernel_ms", "algorithmic_bytes", "step_frac")}}}
         for other in ("ascii95_m16_64MiB", "bytes256_m4_4GiB", "bytes256_m16_4GiB", "bytes256_m128_4GiB", "aaa_1GiB", "ascii95_m64_shard"):
             configs[other] = measure_config(bmx, torch, other, dev, local, args, peak)
+            torch.cuda.empty_cache()
+        for c in configs.values():
+            c["baseline_config"] = True
+        for other in EXTRA_CONFIGS:      # mid-density and short-pattern cases (see WORKLOADS)
+            configs[other] = measure_config(bmx, torch, other, dev, local, args, peak)
+            configs[other]["baseline_config"] = False
             torch.cuda.empty_cache()
 
     if rank == 0:
