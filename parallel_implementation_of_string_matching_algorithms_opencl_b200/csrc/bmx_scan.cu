@@ -724,8 +724,10 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     // ------------------------------------------------------------------ producer warp
     if (warp == kConsumerWarps) {
         if (lane != 0) return;
-        for (uint32_t it = 1;; ++it) {
-            const uint32_t s = it % S;
+        // slot and phase of round `it` are it % S and (it / S) & 1, kept incrementally (S is a runtime value: the division
+        // cost ~25 instructions per tile in every warp)
+        uint32_t s = 1u % S, ph = (1u / S) & 1u;
+        for (;; s = (s + 1u == S) ? 0u : s + 1u, ph ^= (s == 0u) ? 1u : 0u) {
             const uint32_t tile = next_tile;
             bool live = tile < A.num_tiles;
             if (!POSITIONS && A.find_epoch && live) {  // find-first: nothing at or behind a tile that starts past the best hit can win
@@ -733,7 +735,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                 if (found >= 0 && (long long)tile * TILE + OFFS + A.pos_bias > found) live = false;
             }
             if (live) next_tile = gridDim.x + atomicAdd(A.tile_counter, 1u);  // ticket for the next round, in flight during the wait
-            mbar_wait(&ctl->empty[s], ((it / S) & 1u) ^ 1u);
+            mbar_wait(&ctl->empty[s], ph ^ 1u);
             if (!live) {
                 ctl->slot_tile[s] = -1;
                 mbar_arrive(&ctl->full[s]);
@@ -759,9 +761,8 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     unsigned long long my_count = 0;  // count-only mode
     bool dense_mode = false;          // per warp: candidates in most lanes -> next tile takes dense_tile()
 
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t s = it % S;
-        mbar_wait(&ctl->full[s], (it / S) & 1u);
+    for (uint32_t s = 0u, ph = 0u;; s = (s + 1u == S) ? 0u : s + 1u, ph ^= (s == 0u) ? 1u : 0u) {
+        mbar_wait(&ctl->full[s], ph);
         const int32_t tile_s = ctl->slot_tile[s];
         if (tile_s < 0) break;
         const uint32_t tile = (uint32_t)tile_s;
