@@ -1295,7 +1295,7 @@ __global__ void __launch_bounds__(kExpandThreads) expand_kernel(const __grid_con
             uint32_t flags = mine < units ? (wide ? flag4[mine] : (uint32_t)A.item_flag[mine]) : 0u;
             const uint32_t bsum = mine < units ? A.block_sum[mine / per_block] : 0u;
             if (bsum >= kDenseBlockHits) flags = 0u;   // dense blocks belong to phase 2
-#pragma unroll
+#pragma unroll 1   // (unrolled, the four copies of expand_item made a 21 000-instruction kernel: cold instruction fetches sit in every call's latency chain)
             for (uint32_t k = 0; k < 4; ++k) {
                 uint32_t vote = __ballot_sync(0xFFFFFFFFu, ((flags >> (8 * k)) & 0xFFu) != 0u);
                 while (vote) {
