@@ -585,6 +585,7 @@ __device__ __forceinline__ unsigned long long dense_tile_body(const ScanArgs &A,
     constexpr int OFFS = (VARIANT == kQgram || VARIANT == kMulti) ? -3 : 0;
     unsigned long long found = 0;
     uint32_t cand_lanes = 0, tile_total = 0;
+    const uint32_t tile_seg0 = (uint32_t)(tile_v0 / kSegBytes);   // 32-bit segment index of the tile's first segment
     for (int sg = 0; sg < WARP_BYTES / kSegBytes; ++sg) {
         const uint32_t seg_off = warp * WARP_BYTES + sg * kSegBytes;
         const int64_t seg_p0 = tile_v0 + seg_off + lane * 16 + OFFS;
@@ -609,10 +610,10 @@ __device__ __forceinline__ unsigned long long dense_tile_body(const ScanArgs &A,
         const uint32_t hit_lanes = __ballot_sync(0xFFFFFFFFu, seg_hits != 0);
         found += seg_hits;
         if (!POSITIONS && A.find_epoch && hit_lanes) report_first(A, hm, tile_v0 + seg_off + OFFS, lane);
-        if (POSITIONS && hit_lanes) tile_total += publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
+        if (POSITIONS && hit_lanes) tile_total += publish_segment(A, tile_seg0 + seg_off / kSegBytes, hm, seg_hits, lane);
     }
     if (POSITIONS && tile_total && lane == 0)
-        atomicAdd(&A.block_sum[(uint32_t)((tile_v0 + warp * WARP_BYTES) / kBlockBytes)], tile_total);
+        atomicAdd(&A.block_sum[tile_seg0 / kBlockSegs], tile_total);   // a tile lies inside one 2 MiB block
     return found | (cand_lanes >= A.dense_lanes * (WARP_BYTES / kSegBytes) ? (1ull << 63) : 0ull);
 }
 // Out of line for the kernels that verify (their common path must stay exactly the sparse filter loop); the m = 1 and
@@ -768,6 +769,7 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
         const uint32_t tile = (uint32_t)tile_s;
         const uint8_t *st = stages + (size_t)s * A.stage_stride + kPre;  // st[0] = first byte of the tile
         const int64_t tile_v0 = (int64_t)tile * TILE;
+        const uint32_t tile_seg0 = tile * (uint32_t)(TILE / kSegBytes);   // 32-bit segment index of the tile's first segment
         const uint8_t *vbase = A.verify_smem ? (st - tile_v0) : A.vtext;  // text(v) = vbase[v]
         // every start position owned by this tile may be reported (false only at the text's ends)
         const bool all_valid = tile_v0 + OFFS >= A.vmin && tile_v0 + (TILE - 1) + OFFS <= A.vmax;
@@ -860,11 +862,11 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
                     if (!POSITIONS) {
                         my_count += seg_hits;
                         if (A.find_epoch) report_first(A, hm, tile_v0 + seg_off + OFFS, lane);
-                    } else tile_total += publish_segment(A, (uint32_t)((tile_v0 + seg_off) / kSegBytes), hm, seg_hits, lane);
+                    } else tile_total += publish_segment(A, tile_seg0 + seg_off / kSegBytes, hm, seg_hits, lane);
                 }
             }
             if (POSITIONS && tile_total && lane == 0)  // a warp's 4 KiB of a tile lie inside one 2 MiB block
-                atomicAdd(&A.block_sum[(uint32_t)((tile_v0 + warp * WARP_BYTES) / kBlockBytes)], tile_total);
+                atomicAdd(&A.block_sum[tile_seg0 / kBlockSegs], tile_total);   // a tile lies inside one 2 MiB block
             dense_mode = cand_lanes >= A.dense_lanes * SEGS;  // takes effect with the next tile
         }
         // every lane is done reading the stage: hand it back to the producer
