@@ -61,7 +61,9 @@ struct ScanArgs {
     uint32_t hmul;          // QGRAM: hash multiplier K << (32 - 8*(q-4)); the shift drops the bytes beyond the q-gram
     uint32_t hmulr[4];      // QGRAM, 7 <= m <= 10: one multiplier per residue (residue r sees min(8, m - r) bytes)
     uint32_t mulc;          // WINDOW: 2^(32-8q), drops the bytes beyond q
-    uint32_t bcast[3];      // WINDOW, m <= 3: pattern byte k replicated into the four bytes of a word
+    uint32_t bcast[5];      // WINDOW, byte-parallel kernels: pattern byte k replicated into the four bytes of a word
+    uint32_t pat_distinct;  // distinct byte values among the pattern's first 16 bytes (the only hint of the text's alphabet)
+    uint32_t window5;       // WINDOW, m = 5, 6 on small alphabets: byte-parallel test of the first five bytes (plan_scan)
     // per-pattern block in global memory
     const uint8_t *g_pat;
     const int32_t *g_bad;

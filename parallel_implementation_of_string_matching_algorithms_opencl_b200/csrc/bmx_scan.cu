@@ -310,12 +310,14 @@ __device__ __forceinline__ uint32_t window_at(uint32_t lo, uint32_t hi, int s)
 // byte) has a zero byte exactly where all m bytes match; (z & 0x7F..) + 0x7F.. never carries across bytes, so the zero
 // test is exact.  Returns 0x80 in the byte of every matching start position: 3 + 2(m-1) + 3 instructions for four
 // positions instead of a funnel shift, a multiply, a compare and a select each.
-template <int M>   // M = pattern length 1..3: a compile-time constant, so the construction below is branch-free
-__device__ __forceinline__ uint32_t window_flags(uint32_t lo, uint32_t hi, uint32_t b0, uint32_t b1, uint32_t b2)
+template <int M>   // M = bytes tested, 1..5: a compile-time constant, so the construction below is branch-free
+__device__ __forceinline__ uint32_t window_flags(uint32_t lo, uint32_t hi, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3 = 0u, uint32_t b4 = 0u)
 {
     uint32_t z = lo ^ b0;
     if (M >= 2) z |= __funnelshift_r(lo, hi, 8) ^ b1;
     if (M >= 3) z |= __funnelshift_r(lo, hi, 16) ^ b2;
+    if (M >= 4) z |= __funnelshift_r(lo, hi, 24) ^ b3;
+    if (M >= 5) z |= hi ^ b4;   // the byte four positions on is the same byte of the next word
     const uint32_t a = (z & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
     return ~(a | z) & 0x80808080u;
 }
@@ -353,11 +355,11 @@ __device__ __forceinline__ bool filter_any(const uint4 &w, uint32_t w4, const Sc
         any |= (h3 == f0) | (h3 == f1) | (h3 == f2) | (h3 == f3);
         return any;
     } else {
-        if (FLAG >= 2) {   // m = FLAG - 1 <= 3
-            constexpr int M = FLAG >= 2 ? FLAG - 1 : 1;
-            const uint32_t b0 = A.bcast[0], b1 = A.bcast[1], b2 = A.bcast[2];
-            return (window_flags<M>(w.x, w.y, b0, b1, b2) | window_flags<M>(w.y, w.z, b0, b1, b2) | window_flags<M>(w.z, w.w, b0, b1, b2) |
-                    window_flags<M>(w.w, w4, b0, b1, b2)) != 0u;
+        if (FLAG >= 2) {   // m = FLAG - 1 <= 3, or (FLAG 6) the first five bytes of a 5- or 6-byte pattern
+            constexpr int M = FLAG == 6 ? 5 : (FLAG >= 2 ? FLAG - 1 : 1);
+            const uint32_t b0 = A.bcast[0], b1 = A.bcast[1], b2 = A.bcast[2], b3 = A.bcast[3], b4 = A.bcast[4];
+            return (window_flags<M>(w.x, w.y, b0, b1, b2, b3, b4) | window_flags<M>(w.y, w.z, b0, b1, b2, b3, b4) |
+                    window_flags<M>(w.z, w.w, b0, b1, b2, b3, b4) | window_flags<M>(w.w, w4, b0, b1, b2, b3, b4)) != 0u;
         }
         const uint32_t tg = A.f[0];
         const uint32_t ww[5] = {w.x, w.y, w.z, w.w, w4};
@@ -390,10 +392,10 @@ __device__ __forceinline__ uint32_t filter_mask(const uint4 &w, uint32_t w4, con
     } else if (FLAG >= 2) {
         // m = FLAG - 1 <= 3: flags of two words share one multiply that gathers their eight 0x80 bits into one byte
         // ((c0 >> 4 | c1) * 0x204081 >> 24: bits 3,11,19,27 and 7,15,23,31 land on 24..31 in position order, no carries)
-        constexpr int M = FLAG >= 2 ? FLAG - 1 : 1;
-        const uint32_t b0 = A.bcast[0], b1 = A.bcast[1], b2 = A.bcast[2];
-        const uint32_t c0 = window_flags<M>(ww[0], ww[1], b0, b1, b2), c1 = window_flags<M>(ww[1], ww[2], b0, b1, b2);
-        const uint32_t c2 = window_flags<M>(ww[2], ww[3], b0, b1, b2), c3 = window_flags<M>(ww[3], ww[4], b0, b1, b2);
+        constexpr int M = FLAG == 6 ? 5 : (FLAG >= 2 ? FLAG - 1 : 1);
+        const uint32_t b0 = A.bcast[0], b1 = A.bcast[1], b2 = A.bcast[2], b3 = A.bcast[3], b4 = A.bcast[4];
+        const uint32_t c0 = window_flags<M>(ww[0], ww[1], b0, b1, b2, b3, b4), c1 = window_flags<M>(ww[1], ww[2], b0, b1, b2, b3, b4);
+        const uint32_t c2 = window_flags<M>(ww[2], ww[3], b0, b1, b2, b3, b4), c3 = window_flags<M>(ww[3], ww[4], b0, b1, b2, b3, b4);
         mask = ((((c0 >> 4) | c1) * 0x00204081u) >> 24) | (((((c2 >> 4) | c3) * 0x00204081u) >> 24) << 8);
     } else {
 #pragma unroll
@@ -752,9 +754,9 @@ __global__ void __launch_bounds__(kThreads, 2) scan_kernel(const __grid_constant
     const int32_t *bad = A.pat_smem ? ctl->bad : A.g_bad;
     const int32_t *good = A.pat_smem ? ctl->good : A.g_good;
     const uint32_t *rpat = A.pat_smem ? ctl->rpat : nullptr;
-    const bool exact_filter = (VARIANT == kShiftAnd) || (VARIANT == kWindow && A.m <= 4);
+    const bool exact_filter = (VARIANT == kShiftAnd) || (VARIANT == kWindow && (A.m <= 4 || (FULL8 == 6 && A.m == 5)));
     // flagged chunks are checked by the whole warp when pattern and window both sit in shared memory (m <= kPatSmemMax)
-    constexpr bool kNeverVerifies = (VARIANT == kShiftAnd) || (VARIANT == kWindow && FULL8 >= 2);   // m <= 3: the filter is exact
+    constexpr bool kNeverVerifies = (VARIANT == kShiftAnd) || (VARIANT == kWindow && FULL8 >= 2 && FULL8 <= 4);   // m <= 3: the filter is exact
     const bool coop = !kNeverVerifies && !exact_filter && A.pat_smem != 0u && A.verify_smem != 0u && A.coop_verify != 0u;
     const uint32_t *patw = reinterpret_cast<const uint32_t *>(ctl->pat);
     CoopLane cl{};
@@ -1433,6 +1435,13 @@ static uint32_t le_word(const unsigned char *p, int nbytes)
 
 void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, ScanArgs *a)
 {
+    {
+        bool seen[256] = {false};
+        uint32_t distinct = 0;
+        for (int i = 0; i < m && i < 16; ++i)
+            if (!seen[pat[i]]) { seen[pat[i]] = true; ++distinct; }
+        a->pat_distinct = distinct;
+    }
     a->f[0] = a->f[1] = a->f[2] = a->f[3] = 0;
     a->hmul = kHashMul;
     a->mulc = 1u;
@@ -1461,7 +1470,7 @@ void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, Sca
             }
         }
     } else if (variant == BMX_VARIANT_WINDOW) {
-        for (int k = 0; k < 3; ++k) a->bcast[k] = (uint32_t)pat[std::min(k, m - 1)] * 0x01010101u;
+        for (int k = 0; k < 5; ++k) a->bcast[k] = (uint32_t)pat[std::min(k, m - 1)] * 0x01010101u;
         const int q = std::min(m, 4);
         a->mulc = q >= 4 ? 1u : (1u << (32 - 8 * q));
         a->f[0] = le_word(pat, q) * a->mulc;
@@ -1470,10 +1479,10 @@ void fill_filter_constants(int variant, const unsigned char *pat, int32_t m, Sca
 
 // FULL8: WINDOW compares whole 4-byte windows (m >= 4); QGRAM hashes all residues with one multiplier.
 // The kernels' FLAG parameter: QGRAM 1 = one multiplier for all residues; WINDOW 1 = whole 4-byte windows (m >= 4),
-// 2 / 3 / 4 = m of 1 / 2 / 3 bytes; everything else 1.
+// 2 / 3 / 4 = m of 1 / 2 / 3 bytes, 6 = five bytes at once (m = 5, 6 on small alphabets); everything else 1.
 static int uses_full8(int variant, const ScanArgs &a)
 {
-    if (variant == BMX_VARIANT_WINDOW) return a.m >= 4 ? 1 : a.m + 1;
+    if (variant == BMX_VARIANT_WINDOW) return a.m >= 4 ? (a.window5 ? 6 : 1) : a.m + 1;
     if (variant == BMX_VARIANT_QGRAM)
         return (a.hmulr[0] == a.hmulr[3] && a.hmulr[1] == a.hmulr[3] && a.hmulr[2] == a.hmulr[3]) ? 1 : 0;
     return 1;
@@ -1497,6 +1506,7 @@ static const void *pick_kernel_tile(int variant, int full8, bool positions)
         case 2: return positions ? kernel_ptr<kWindow, 2, TILE, true>() : kernel_ptr<kWindow, 2, TILE, false>();
         case 3: return positions ? kernel_ptr<kWindow, 3, TILE, true>() : kernel_ptr<kWindow, 3, TILE, false>();
         case 4: return positions ? kernel_ptr<kWindow, 4, TILE, true>() : kernel_ptr<kWindow, 4, TILE, false>();
+        case 6: return positions ? kernel_ptr<kWindow, 6, TILE, true>() : kernel_ptr<kWindow, 6, TILE, false>();
         default: return positions ? kernel_ptr<kWindow, 1, TILE, true>() : kernel_ptr<kWindow, 1, TILE, false>();
         }
     }
@@ -1584,9 +1594,14 @@ int plan_scan(int device, int variant, int32_t m, bool positions, ScanArgs *a, S
     a->num_blocks = (a->num_segs + kBlockSegs - 1) / kBlockSegs;
     a->owner_offset = (variant == BMX_VARIANT_QGRAM || multi) ? -3 : 0;
     a->coop_verify = env_int("BMX_COOP_VERIFY", 1) != 0 ? 1u : 0u;   // measurement knob
+    // WINDOW on m = 5, 6: the 4-byte window passes 1 in 256 positions of a 4-letter text and the scan becomes
+    // verification-bound (DNA: 2.0 / 2.2 TB/s).  The byte-parallel construction of the m <= 3 kernels, extended to five
+    // bytes (11 instructions per word instead of 7, exact for m = 5), is chosen when the pattern has <= 4 distinct
+    // bytes -- the same proxy for the text's alphabet as in the q-gram layout choice.  BMX_WINDOW5=0/1 forces either.
+    a->window5 = (variant == BMX_VARIANT_WINDOW && (m == 5 || m == 6) && env_int("BMX_WINDOW5", a->pat_distinct <= 4 ? 1 : 0) != 0) ? 1u : 0u;
     // Patterns whose flagged chunks are checked by the whole warp never gain from the dense path (profiles/verify_ab_r02.txt:
     // equal or faster at every density measured): 33 lanes = never.
-    const bool verifies = !(variant == BMX_VARIANT_SHIFTAND || (variant == BMX_VARIANT_WINDOW && m <= 4));
+    const bool verifies = !(variant == BMX_VARIANT_SHIFTAND || (variant == BMX_VARIANT_WINDOW && (m <= 4 || (a->window5 && m == 5))));
     const bool coop = verifies && a->coop_verify && a->pat_smem && a->verify_smem;
     a->dense_lanes = (uint32_t)std::max(1, std::min(33, env_int("BMX_DENSE_LANES", coop ? 33 : (int)(m >= 16 ? kDenseLanesLong : kDenseLanesShort))));
     // BMX_SPARE_SMS leaves SMs free for concurrently running kernels (the NCCL collectives of a
