@@ -367,6 +367,8 @@ void ThreadCtx::release_buffers()
             bounce[i] = nullptr;
         }
         bounce_bytes = 0;
+        if (h_small) cudaFreeHost(h_small);
+        h_small = nullptr;
     }
     if (have) cudaSetDevice(keep);
     (void)cudaGetLastError();

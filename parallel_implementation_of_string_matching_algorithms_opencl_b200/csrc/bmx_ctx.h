@@ -28,6 +28,7 @@ namespace bmx {
 
 constexpr int kMaxDevices = 64;
 constexpr int kBounce = 3;
+constexpr int64_t kSmallSpec = 8192;   // positions read back together with the count (64 KiB)
 
 struct DevBuf {
     void *p = nullptr;
@@ -42,6 +43,7 @@ struct ThreadCtx {
     unsigned char *bounce[kBounce] = {nullptr, nullptr, nullptr};
     size_t bounce_bytes = 0;
     DevBuf text, pos, misc, aux;
+    int64_t *h_small = nullptr;   // pinned landing area for the speculative result read of small host texts (kSmallSpec entries)
     ThreadCtx() = default;
     ThreadCtx(const ThreadCtx &) = delete;
     ThreadCtx &operator=(const ThreadCtx &) = delete;

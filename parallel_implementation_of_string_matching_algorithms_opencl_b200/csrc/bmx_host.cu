@@ -96,6 +96,54 @@ int scan_resident(ThreadCtx &c, const unsigned char *d_text, int64_t n, const ch
     return BMX_OK;
 }
 
+// Small host texts -- the reference's own fixtures are 60 B .. 560 KB (BoyreMoore/**/input*.txt) and its timed window
+// is one launch plus an 8-byte read (BoyreMoore.cpp:258-290) -- are latency, not bandwidth: everything goes through ONE
+// stream (no copy stream, no events, no pinned-memory query), and the first kSmallSpec positions travel back to a pinned
+// landing area right behind the kernels, so that the call synchronises once instead of twice (count, then positions).
+// Falls back to the resident re-scan when the text holds more hits than the position buffer (scan_resident).
+constexpr int64_t kSmallHostBytes = int64_t(4) << 20;
+int small_host_search(ThreadCtx &c, int device, const char *text, int64_t n, const char *pat, int32_t m, int32_t variant,
+                      int64_t *pos_out, int64_t want_cap, uint64_t *count_out, bmx_stats *stats)
+{
+    if (int rc = ensure_streams(c, device, 0)) return rc;
+    if (int rc = ensure_buf(c, c.text, (size_t)n + 16)) return rc;
+    int64_t cap = first_pos_cap(n, m, want_cap);
+    if ((int64_t)(c.pos.cap / 8) > cap) cap = std::min<int64_t>(want_cap, (int64_t)(c.pos.cap / 8));
+    if (cap > 0)
+        if (int rc = ensure_buf(c, c.pos, (size_t)cap * 8)) return rc;
+    if (cap > 0 && !c.h_small) BMX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&c.h_small), (size_t)kSmallSpec * 8, cudaHostAllocDefault));
+    cudaStream_t st = c.scan_stream;
+    unsigned char *d_text = static_cast<unsigned char *>(c.text.p);
+    // (a pageable source is staged by the runtime before the call returns: the caller's buffer is free afterwards)
+    BMX_CUDA(cudaMemcpyAsync(d_text, text, (size_t)n, cudaMemcpyHostToDevice, st));
+    int rc = bmx_scanner_set_pattern(c.scanner, pat, m, variant, st);
+    if (rc == BMX_OK) rc = bmx_scanner_begin(c.scanner, cap > 0 ? static_cast<int64_t *>(c.pos.p) : nullptr, cap, st);
+    if (rc == BMX_OK) rc = bmx_scanner_scan(c.scanner, d_text, n, 0, st);
+    if (rc != BMX_OK) return rc;
+    const int64_t spec = std::min<int64_t>(cap, kSmallSpec);
+    if (spec > 0) BMX_CUDA(cudaMemcpyAsync(c.h_small, c.pos.p, (size_t)spec * 8, cudaMemcpyDeviceToHost, st));
+    uint64_t count = 0;
+    if ((rc = bmx_scanner_finish(c.scanner, &count, stats, st)) != BMX_OK) return rc;   // the one synchronisation
+    *count_out = count;
+    int64_t dev_cap = cap;
+    const int64_t need = std::min<int64_t>(want_cap, (int64_t)count);
+    if (need > cap) {   // denser than the buffer: the text is resident, scan it again with room for what the caller asked for
+        if ((rc = scan_resident(c, d_text, n, pat, m, variant, 0, want_cap, &count, &dev_cap, stats)) != BMX_OK) return rc;
+        *count_out = count;
+        BMX_CUDA(cudaMemcpyAsync(pos_out, c.pos.p, (size_t)std::min<int64_t>({(int64_t)count, dev_cap, want_cap}) * 8, cudaMemcpyDeviceToHost, st));
+        BMX_CUDA(cudaStreamSynchronize(st));
+        return BMX_OK;
+    }
+    if (need > 0) {
+        memcpy(pos_out, c.h_small, (size_t)std::min(need, spec) * 8);
+        if (need > spec) {
+            BMX_CUDA(cudaMemcpyAsync(pos_out + spec, static_cast<int64_t *>(c.pos.p) + spec, (size_t)(need - spec) * 8, cudaMemcpyDeviceToHost, st));
+            BMX_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    return BMX_OK;
+}
+
 struct Ingest {
     // in
     int64_t want_cap = 0;        // positions the caller can use (0: count only)
@@ -311,6 +359,8 @@ int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int3
     *count_out = 0;
     if (stats) *stats = bmx_stats{};
     if (n < m) return BMX_OK;
+    if (n <= kSmallHostBytes && env_long("BMX_SMALL_HOST", 1) != 0 && env_long("BMX_RESIDENT_MAX_MB", -1) < 0 && env_long("BMX_H2D_CHUNK_KB", 0) == 0)
+        return small_host_search(*c, device, text, n, pat, m, variant, pos_out, pos_out ? std::min(pos_cap, n - m + 1) : 0, count_out, stats);
     Ingest io;
     io.want_cap = pos_out ? std::min(pos_cap, n - m + 1) : 0;
     if (int rc = ingest_and_scan(*c, device, text, n, pat, m, 0, variant, &io)) return rc;
