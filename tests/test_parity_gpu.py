@@ -851,3 +851,36 @@ def test_cooperative_verification_edges(bmx, oracle, dev, monkeypatch):
         want = oracle.search_np(per, pat, threads=-1)
         count, got, _ = gpu_positions(bmx, td, pat, cap=want.size + 1)
         assert count == want.size and np.array_equal(got, want), pat
+
+
+def test_small_host_text_latency_path(bmx, oracle, monkeypatch):
+    """Host texts of at most 4 MiB take the one-stream path with a speculative read-back of the first 8192 positions
+    (bmx_host.cu: small_host_search).  Its branches: fewer hits than the read-back, more hits than the read-back, more
+    hits than the device buffer (re-scan of the resident copy), count-only, a truncating caller buffer, pinned and
+    pageable sources, sizes around the limit -- each against the oracle and against the chunked path."""
+    rng = np.random.default_rng(314)
+    cases = []
+    sparse = rng.integers(0, 95, size=700_001, dtype=np.uint8) + 32
+    pat = b"needle in a haystack"
+    for o in (0, 5000, 123_456, 700_001 - len(pat)):
+        sparse[o:o + len(pat)] = np.frombuffer(pat, dtype=np.uint8)
+    cases.append((sparse, pat))                                              # a handful of hits
+    cases.append((rng.integers(0, 2, size=300_000, dtype=np.uint8) + 97, b"ab"))     # ~75 000 hits: beyond the read-back
+    cases.append((np.full(3_000_000, ord("a"), dtype=np.uint8), b"aa"))              # 3 M hits: beyond the first device buffer
+    cases.append((rng.integers(0, 4, size=(4 << 20), dtype=np.uint8) + 65, b"ACGTAC"))   # exactly the size limit
+    cases.append((rng.integers(0, 4, size=(4 << 20) + 1, dtype=np.uint8) + 65, b"ACGTAC"))   # one byte more: the chunked path
+    cases.append((np.frombuffer(b"abc", dtype=np.uint8).copy(), b"abcd"))            # m > n
+    for text, p in cases:
+        want = oracle.search_np(text, p, threads=-1) if text.size >= len(p) else np.zeros(0, dtype=np.int64)
+        pinned = torch.from_numpy(text.copy()).pin_memory()
+        for src in (text, pinned):
+            for small in ("1", "0"):
+                monkeypatch.setenv("BMX_SMALL_HOST", small)
+                count, got = bmx.search(src, p)
+                assert count == want.size and np.array_equal(got, want), (text.size, p, small)
+                count, got = bmx.search(src, p, max_positions=0)
+                assert count == want.size and got.size == 0
+                cap = max(1, want.size // 3)
+                count, got = bmx.search(src, p, max_positions=cap)
+                assert count == want.size and np.array_equal(got, want[:cap]), (text.size, p, small, "truncated")
+    monkeypatch.delenv("BMX_SMALL_HOST")
