@@ -359,6 +359,14 @@ int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int3
     *count_out = 0;
     if (stats) *stats = bmx_stats{};
     if (n < m) return BMX_OK;
+    // CUDA-event instrumentation only when the caller asks for the times: the records cost ~15 us per call
+    // (profiles/call_latency_r02.txt), which is nothing for 4 GiB and a fifth of a call on the reference's 500 KB fixture
+    struct TimingGuard {
+        bmx_scanner *s;
+        int keep;
+        TimingGuard(bmx_scanner *sc, int level) : s(sc), keep(sc->timing_level) { s->timing_level = level; }
+        ~TimingGuard() { s->timing_level = keep; }
+    } timing_guard(c->scanner, stats ? 2 : 0);
     if (n <= kSmallHostBytes && env_long("BMX_SMALL_HOST", 1) != 0 && env_long("BMX_RESIDENT_MAX_MB", -1) < 0 && env_long("BMX_H2D_CHUNK_KB", 0) == 0)
         return small_host_search(*c, device, text, n, pat, m, variant, pos_out, pos_out ? std::min(pos_cap, n - m + 1) : 0, count_out, stats);
     Ingest io;

@@ -69,6 +69,40 @@ int main(int argc, char **argv)
     memcpy(pinned, text.data(), (size_t)n);
     printf("bmx_search, positions          (pinned host)     %8.1f us per call\n",
            us_per_call([&] { bmx_search(pinned, n, pat.data(), m, h_pos.data(), cap, &count); }, reps / 4 + 1));
+    {
+        // the same steps by hand through the streaming scanner API on one stream: the floor of the host path
+        bmx_scanner *sc = nullptr;
+        cudaStream_t st;
+        cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+        int64_t *h_land = nullptr;
+        cudaHostAlloc(reinterpret_cast<void **>(&h_land), 8192 * 8, cudaHostAllocDefault);
+        if (bmx_scanner_create(0, &sc) == BMX_OK) {
+            bmx_scanner_set_pattern(sc, pat.data(), m, BMX_VARIANT_AUTO, st);
+            printf("by hand: H2D + scanner + D2H, one stream (pinned)  %6.1f us per call\n",
+                   us_per_call([&] {
+                       cudaMemcpyAsync(d_text, pinned, (size_t)n, cudaMemcpyHostToDevice, st);
+                       bmx_scanner_set_pattern(sc, pat.data(), m, BMX_VARIANT_AUTO, st);
+                       bmx_scanner_begin(sc, d_pos, cap, st);
+                       bmx_scanner_scan(sc, d_text, n, 0, st);
+                       cudaMemcpyAsync(h_land, d_pos, 8192 * 8, cudaMemcpyDeviceToHost, st);
+                       bmx_scanner_finish(sc, &count, nullptr, st);
+                   }, reps / 4 + 1));
+            printf("by hand: scanner only (resident), own stream       %6.1f us per call\n",
+                   us_per_call([&] {
+                       bmx_scanner_begin(sc, d_pos, cap, st);
+                       bmx_scanner_scan(sc, d_text, n, 0, st);
+                       bmx_scanner_finish(sc, &count, nullptr, st);
+                   }, reps / 4 + 1));
+            printf("by hand: H2D + scanner, one stream (pinned)        %6.1f us per call\n",
+                   us_per_call([&] {
+                       cudaMemcpyAsync(d_text, pinned, (size_t)n, cudaMemcpyHostToDevice, st);
+                       bmx_scanner_begin(sc, d_pos, cap, st);
+                       bmx_scanner_scan(sc, d_text, n, 0, st);
+                       bmx_scanner_finish(sc, &count, nullptr, st);
+                   }, reps / 4 + 1));
+            bmx_scanner_destroy(sc);
+        }
+    }
     printf("first match at %lld, last count %llu\n", (long long)first, (unsigned long long)count);
     return 0;
 }
