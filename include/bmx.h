@@ -47,8 +47,8 @@ typedef enum bmx_status {
 /* Scan variants.  AUTO picks by pattern length from measured throughput. */
 typedef enum bmx_variant {
     BMX_VARIANT_AUTO = 0,
-    BMX_VARIANT_QGRAM = 1,    /* m >= 7: aligned q-gram hash filter + warp ballot + BM-skip verify */
-    BMX_VARIANT_WINDOW = 2,   /* any m : per-position <=4-byte window filter (+ BM-skip verify) */
+    BMX_VARIANT_QGRAM = 1,    /* m >= 7: aligned q-gram hash filter + warp ballot + warp-cooperative verify (BM-skip walk beyond m = 1024) */
+    BMX_VARIANT_WINDOW = 2,   /* any m : window filter, exact for m <= 4 (m = 5 on small alphabets), else + verify */
     BMX_VARIANT_SHIFTAND = 3  /* m <= 32: bit-parallel Shift-And (the Shift-Or family) */
 } bmx_variant;
 
@@ -102,12 +102,14 @@ int bmx_build_tables(const char *pat, int32_t m, int32_t bad[256], int32_t *good
  * written (the smallest ones); pos_out may be NULL for count-only.  m > n is not an error
  * (count 0, kernel1.cl:15,19); m <= 0 is BMX_E_BADARG.  Synchronous.  The host->device copy is
  * chunked and overlapped with scanning (pinned memory is used directly, pageable memory goes
- * through pinned bounce buffers).
+ * through pinned bounce buffers); texts of at most 4 MiB -- the size of the reference's own
+ * fixtures -- take a one-stream latency path with a single synchronisation instead.
  */
 int bmx_search(const char *text, int64_t n, const char *pat, int32_t m,
                int64_t *pos_out, int64_t pos_cap, uint64_t *count_out);
 
-/* As bmx_search, on an explicit device, with variant choice and measurements. */
+/* As bmx_search, on an explicit device, with variant choice and measurements.  CUDA events are recorded only
+ * when stats is non-NULL (they cost ~15 us per call). */
 int bmx_search_ex(int device, const char *text, int64_t n, const char *pat, int32_t m,
                   int64_t *pos_out, int64_t pos_cap, uint64_t *count_out,
                   int32_t variant, bmx_stats *stats);
