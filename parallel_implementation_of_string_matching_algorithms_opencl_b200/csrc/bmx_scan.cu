@@ -10,10 +10,12 @@
 //                   [16 B pre | TILE | halo] of text per tile into a ring of shared-memory
 //                   stages with 1-D TMA bulk copies (cp.async.bulk ... mbarrier::complete_tx).
 //   consumer warps  8 warps read the stage with 16-byte LDS.128, run a branch-free candidate
-//                   filter over 16 start positions per thread, vote with __ballot_sync, and only
-//                   lanes holding candidates verify them right-to-left with the reference's
-//                   bad-symbol / good-suffix shifts (kernel1.cl:21-33) pruning their own
-//                   candidate bits.
+//                   filter over 16 start positions per thread and vote with __ballot_sync; a chunk
+//                   with candidates is then checked by the whole warp at once (coop_verify16:
+//                   16 start positions x 2 pattern words per ballot).  Patterns that do not fit
+//                   shared memory (m > 1024) are verified by the flagged lanes right-to-left with
+//                   the reference's bad-symbol / good-suffix shifts (kernel1.cl:21-33) pruning
+//                   their own candidate bits (verify_candidates).
 //   emission        every thread holds a 16-bit hit mask per 16-byte chunk.  Warps whose 2 KiB
 //                   segment has hits store the masks (mask16) and the segment's hit count
 //                   (seg_count, block_sum); no CTA ever waits for another one.  The CTA
@@ -27,8 +29,9 @@
 //   QGRAM    m >= 7.  Any occurrence covers the aligned 32-bit word at ceil(p/4)*4 and the word
 //            after it; h = W[j] + hmul * W[j+1] is compared with the 4 pattern hashes for
 //            r = (4 - p%4)%4.  1 IMAD + 4 ISETP per 4 text bytes, no funnel shifts.
-//   WINDOW   any m.  The <=4-byte window at every position (funnel shifts) against P[0..q).
-//            Exact for m <= 4.
+//   WINDOW   any m.  m >= 4: the 4-byte window at every position (funnel shifts) against P[0..4), exact
+//            for m = 4.  m <= 3, and m = 5, 6 on small alphabets: four start positions per word at once
+//            (zero-byte detection over the XOR with the replicated pattern bytes), exact up to five bytes.
 //   SHIFTAND m <= 32. Bit-parallel Shift-And (the Shift-Or family): D = ((D<<1)|1) & B[c].
 //            Kept because the north star asks for the comparison; measured slower.
 #include <cuda_runtime.h>
